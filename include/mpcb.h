@@ -1,0 +1,173 @@
+/*
+ * mpcb.h — C-ABI of the B200-native batched NMPC (PANOC + ALM/PM) solver.
+ *
+ * This is the drop-in boundary for the ONE hot path of
+ * Woodenonez/DyObAv-MPCnWTA-Warehouse: the OpEn-generated solver that
+ * `src/pkg_mpc_tracker/trajectory_tracker.py:61-62` loads and `:362` calls
+ * (`self.solver.run(parameters)`).  The reference's generated extension is a
+ * PyO3 module wrapping `solve(p, cache, u, y0, c0)`; these entry points are
+ * what a binding for that call would bind, batched over B independent
+ * instances.  Plain pointers and sizes only — no torch types.
+ *
+ * All `const double*` / `double*` / `int32_t*` arguments of the *_f64 entry
+ * points are DEVICE pointers (e.g. torch.Tensor.data_ptr()) unless the name
+ * ends in `_host`.  Every function returns 0 on success or a negative
+ * MPCB_E_* code; nothing throws, nothing allocates behind the caller's back
+ * except the *_host convenience path, and all device work is ordered on the
+ * `stream` argument (a cudaStream_t passed as void*).
+ */
+#ifndef MPCB_H
+#define MPCB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPCB_ABI_VERSION 1
+
+/* ---- error codes --------------------------------------------------------- */
+#define MPCB_OK            0
+#define MPCB_E_DIMS       (-1)  /* unsupported / inconsistent dimensions        */
+#define MPCB_E_NULL       (-2)  /* required pointer is NULL                     */
+#define MPCB_E_WORKSPACE  (-3)  /* workspace too small                          */
+#define MPCB_E_CUDA       (-4)  /* CUDA runtime error (see mpcb_last_error)     */
+#define MPCB_E_ALIGN      (-5)  /* pointer not 8-byte aligned                   */
+#define MPCB_E_NO_DEVICE  (-6)  /* no CUDA device / wrong architecture          */
+
+/* ---- per-instance exit status (mirrors OpEn's ExitStatus, the strings that
+ *      config/mpc_fast.yaml:48 `bad_exit_codes` refers to) ------------------- */
+#define MPCB_CONVERGED                   0
+#define MPCB_NOT_CONVERGED_ITERATIONS    1
+#define MPCB_NOT_CONVERGED_OUT_OF_TIME   2  /* never produced: no wall clock on a batch */
+#define MPCB_NOT_FINITE_COMPUTATION      3
+
+/*
+ * Problem dimensions.  The reference fixes these at code-generation time from
+ * config/mpc_*.yaml (`N_hor, Nother, Nstcobs, nstcobs/3, Ndynobs`, lines
+ * 21-31); here they are run-time.  nu=2, ns=3, nq=10, ndynobs=6 are the
+ * unicycle problem's constants (mpc_builder.py:45-58).
+ */
+typedef struct mpcb_dims {
+    int32_t N;       /* horizon N_hor (1..64)                                   */
+    int32_t Nother;  /* other robots                                            */
+    int32_t Nstc;    /* static polygons (half-space form)                       */
+    int32_t nedge;   /* edges per polygon = nstcobs/3 (reference: 4), 1..8      */
+    int32_t Ndyn;    /* dynamic-obstacle ellipses per time offset               */
+} mpcb_dims;
+
+/* Robot / kinematic constants: config/mpc_fast.yaml:6-18 (configs.py:93-103). */
+typedef struct mpcb_robot {
+    double ts;
+    double vehicle_width;   /* fleet safe distance (mpc_builder.py:90,97)       */
+    double vehicle_margin;  /* ellipse inflation   (mpc_builder.py:122,140)     */
+    double social_margin;   /* extra inflation for the t=0 ellipse (:122)       */
+    double lin_vel_min, lin_vel_max;   /* input box U (:151-153)                */
+    double ang_vel_max;
+    double lin_acc_min, lin_acc_max;   /* ALM set C  (:162-166)                 */
+    double ang_acc_max;
+} mpcb_robot;
+
+/*
+ * Solver settings: OpEn SolverConfiguration as the reference leaves it
+ * (mpc_builder.py:187-195): only initial_penalty=10 and the wall-clock cap are
+ * set, the rest are opengen 0.6.13 defaults.
+ */
+typedef struct mpcb_solver_cfg {
+    double tolerance;            /* eps           1e-4                          */
+    double initial_tolerance;    /* eps_0         1e-4                          */
+    double delta_tolerance;      /* delta         1e-4                          */
+    double inner_tol_update;     /* beta          0.1                           */
+    double penalty_update;       /* rho           5.0                           */
+    double sufficient_decrease;  /* theta         0.1                           */
+    double initial_penalty;      /* c0            10.0 (mpc_builder.py:188)     */
+    double sy_epsilon;           /* L-BFGS s'y    1e-10                         */
+    double cbfgs_epsilon;        /* C-BFGS eps    1e-8                          */
+    double cbfgs_alpha;          /* C-BFGS alpha  1.0                           */
+    int32_t max_inner;           /* 500                                         */
+    int32_t max_outer;           /* 10                                          */
+    int32_t lbfgs_mem;           /* 10 (<= MPCB_MAX_LBFGS)                      */
+    int32_t reserved;
+} mpcb_solver_cfg;
+
+#define MPCB_MAX_LBFGS 10
+#define MPCB_MAX_N     64
+#define MPCB_MAX_EDGE  8
+
+/* Length of the parameter vector p for these dims (2778 at the yaml defaults). */
+int32_t mpcb_param_len(const mpcb_dims* dims);
+/* nu*N, n1 (=2N ALM constraints), n2 (=max(Ndyn,1) penalty constraints). */
+int32_t mpcb_num_decision(const mpcb_dims* dims);
+int32_t mpcb_n1(const mpcb_dims* dims);
+int32_t mpcb_n2(const mpcb_dims* dims);
+
+int32_t mpcb_abi_version(void);
+/* Text of the last CUDA error seen by this thread ("" if none). */
+const char* mpcb_last_error(void);
+/* Fill defaults equal to the reference's yaml / opengen defaults. */
+void mpcb_default_robot(mpcb_robot* r);
+void mpcb_default_solver_cfg(mpcb_solver_cfg* c);
+
+/*
+ * Evaluate the augmented cost the inner solver minimises and its pieces, for
+ * B instances:  psi(u; c, y) = f(u) + c/2 [ dist^2_C(F1(u)+y/max(c,1)) + |F2(u)|^2 ].
+ * Replaces the CasADi-generated `cost`, `grad`, `mapping_f1`, `mapping_f2`
+ * C functions the OpEn build emits from mpc_builder.py:171-174.
+ *   p [n_p, np]  reference layout (mpc_builder.py:60), one row per scenario
+ *   u [B, 2N]    B = n_p * starts; instance b uses row b / starts of p
+ *   y [B, n1] or NULL (zeros), c [B] or NULL (initial_penalty)
+ * Outputs (any may be NULL): f[B], psi[B], grad[B,2N], F1[B,n1], F2[B,n2].
+ */
+int32_t mpcb_eval_f64(const mpcb_dims* dims, const mpcb_robot* robot,
+                      const mpcb_solver_cfg* cfg,
+                      int32_t n_p, int32_t starts,
+                      const double* p, const double* u,
+                      const double* y, const double* c,
+                      double* f, double* psi, double* grad,
+                      double* F1, double* F2,
+                      void* stream);
+
+/*
+ * Solve B = n_p*starts independent instances: ALM/PM outer loop around PANOC,
+ * replacing the generated `Solver.run(p, initial_guess,
+ * initial_lagrange_multipliers, initial_penalty)` (trajectory_tracker.py:13-15).
+ *   u0 [B,2N] or NULL (zeros, the reference's behaviour: it passes p only)
+ *   y0 [B,n1] or NULL (zeros);  c0 [B] or NULL (cfg->initial_penalty)
+ * Outputs (u_out, exit_status required; others may be NULL):
+ *   u_out[B,2N] solution, cost[B] (= f(u*)), exit_status[B] (MPCB_* above),
+ *   n_outer[B], n_inner[B], fpr[B] last inner |gamma*fpr|, f1_infeas[B]
+ *   (=|y+ - y|/c), f2_norm[B], penalty[B] final c, y_out[B,n1] multipliers,
+ *   evals[B,2]: number of (cost-only, cost+gradient) horizon evaluations the
+ *   kernel performed — feeds the work/roofline accounting.
+ */
+int32_t mpcb_solve_f64(const mpcb_dims* dims, const mpcb_robot* robot,
+                       const mpcb_solver_cfg* cfg,
+                       int32_t n_p, int32_t starts,
+                       const double* p, const double* u0,
+                       const double* y0, const double* c0,
+                       double* u_out, double* cost, int32_t* exit_status,
+                       int32_t* n_outer, int32_t* n_inner,
+                       double* fpr, double* f1_infeas, double* f2_norm,
+                       double* penalty, double* y_out, int32_t* evals,
+                       void* stream);
+
+/*
+ * Host-buffer convenience for the single-solve path the reference actually
+ * uses (one p list per timestep): copies p (and u0 if given) H2D, solves one
+ * instance, copies the results back, synchronises.  All pointers are HOST.
+ * out_scalars[8] = {cost, fpr, f1_infeas, f2_norm, penalty, n_outer, n_inner,
+ * solve_time_ms (device time of the solve kernel)}.
+ */
+int32_t mpcb_solve_one_host(const mpcb_dims* dims, const mpcb_robot* robot,
+                            const mpcb_solver_cfg* cfg,
+                            const double* p_host, const double* u0_host,
+                            const double* y0_host, const double* c0_host,
+                            double* u_out_host, double* y_out_host,
+                            int32_t* exit_status_host, double* out_scalars);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPCB_H */
