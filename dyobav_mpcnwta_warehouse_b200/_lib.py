@@ -1,0 +1,60 @@
+"""ctypes binding of libmpcb.so (include/mpcb.h).  No CPU fallback: a missing
+library or a missing GPU raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+from .problem import CDims, CRobot, CSolverCfg
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libmpcb.so")
+_lib = None
+
+ERRORS = {-1: "unsupported or inconsistent dimensions", -2: "required pointer is NULL",
+          -3: "workspace too small", -4: "CUDA error", -5: "misaligned pointer",
+          -6: "no CUDA device"}
+
+# every symbol include/mpcb.h declares
+EXPORTS = ("mpcb_abi_version", "mpcb_last_error", "mpcb_param_len", "mpcb_num_decision", "mpcb_n1",
+           "mpcb_n2", "mpcb_default_robot", "mpcb_default_solver_cfg", "mpcb_workspace_bytes",
+           "mpcb_eval_f64", "mpcb_solve_f64", "mpcb_solve_one_host")
+
+
+def load():
+    """Load the CUDA library; raise RuntimeError (never fall back) when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m dyobav_mpcnwta_warehouse_b200.csrc.build`"
+            " (or __graft_entry__.build()); there is no CPU fallback")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, dp = ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p
+    pd, pr, pc = ctypes.POINTER(CDims), ctypes.POINTER(CRobot), ctypes.POINTER(CSolverCfg)
+    L.mpcb_abi_version.restype = i32
+    L.mpcb_last_error.restype = ctypes.c_char_p
+    for name in ("mpcb_param_len", "mpcb_num_decision", "mpcb_n1", "mpcb_n2"):
+        getattr(L, name).restype = i32
+        getattr(L, name).argtypes = [pd]
+    L.mpcb_default_robot.argtypes = [pr]
+    L.mpcb_default_solver_cfg.argtypes = [pc]
+    L.mpcb_workspace_bytes.restype = i32
+    L.mpcb_workspace_bytes.argtypes = [pd, i32, i32, ctypes.POINTER(ctypes.c_size_t)]
+    L.mpcb_eval_f64.restype = i32
+    L.mpcb_eval_f64.argtypes = [pd, pr, pc, i32, i32] + [dp] * 9 + [vp, ctypes.c_size_t, vp]
+    L.mpcb_solve_f64.restype = i32
+    L.mpcb_solve_f64.argtypes = [pd, pr, pc, i32, i32] + [dp] * 15 + [vp, ctypes.c_size_t, vp]
+    L.mpcb_solve_one_host.restype = i32
+    L.mpcb_solve_one_host.argtypes = [pd, pr, pc] + [dp] * 8
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        detail = ""
+        if rc == -4 and _lib is not None:
+            detail = ": " + _lib.mpcb_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what} failed ({rc}: {ERRORS.get(rc, 'unknown error')}{detail})")

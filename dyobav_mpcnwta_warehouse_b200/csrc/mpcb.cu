@@ -1,0 +1,597 @@
+// mpcb.cu — kernels and the C-ABI (include/mpcb.h) of the batched NMPC solver.
+//
+//   K3 stage_kernel : raw parameter rows p (reference AoS layout,
+//                     mpc_builder.py:47-60) -> structure-of-arrays scenario
+//                     blocks in the workspace (cos/sin of ellipse angles,
+//                     inverse squared radii, weights folded in: done once per
+//                     scenario instead of once per cost evaluation).
+//   K2 eval_kernel  : psi / grad psi / F1 / F2 for B instances (parity tests).
+//   K1 solve_kernel : persistent CTAs; each pulls a group of instances from an
+//                     atomic queue, TMA-bulk-loads the scenario block(s) into
+//                     shared memory, and every warp runs the whole ALM/PANOC
+//                     solve of one instance out of registers + shared memory.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false
+// (-fmad=false: only the explicit fma() calls fuse, so the arithmetic does not
+// depend on the compiler's contraction choices).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "mpcb_device.cuh"
+#include "mpcb_solver.cuh"
+
+using namespace mpcb;
+
+namespace {
+
+thread_local char g_err[256] = "";
+
+#define CUDA_TRY(x)                                                                  \
+    do {                                                                             \
+        cudaError_t e_ = (x);                                                        \
+        if (e_ != cudaSuccess) {                                                     \
+            snprintf(g_err, sizeof(g_err), "%s: %s", #x, cudaGetErrorString(e_));    \
+            return MPCB_E_CUDA;                                                      \
+        }                                                                            \
+    } while (0)
+
+// ----------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ------------------------------------------------------------------ K3: staging
+__global__ void __launch_bounds__(128) stage_kernel(const KParams P, const double* __restrict__ p,
+                                                    double* __restrict__ staged)
+{
+    const Lay& L = P.L;
+    const int N = L.N;
+    for (int s = blockIdx.x; s < P.n_p; s += gridDim.x) {
+        const double* pr = p + (size_t)s * L.np;
+        double* S = staged + (size_t)s * L.total;
+        const int tid = threadIdx.x, nt = blockDim.x;
+        // header
+        for (int i = tid; i < H_SIZE; i += nt) {
+            double v = 0.0;
+            if (i <= H_S0T) v = pr[L.p_s0 + i];
+            else if (i <= H_UM1W) v = pr[L.p_um1 + (i - H_UM1V)];
+            else if (i <= H_SNT) v = pr[L.p_sN + (i - H_SNX)];
+            else if (i < H_Q + 10) v = pr[L.p_q + (i - H_Q)];
+            S[L.o_hdr + i] = v;
+        }
+        for (int k = tid; k < N; k += nt) {
+            S[L.o_rv + k] = pr[L.p_rv + k];
+            S[L.o_qstc + k] = pr[L.p_qstc + k];
+            // reference polyline: rows 0..N-1 of r_s, row N duplicates row N-1
+            // (mpc_builder.py:68-69); segment k joins rows k and k+1
+            const int k2 = k + 1 < N ? k + 1 : N - 1;
+            const double ax = pr[L.p_rs + 3 * k], ay = pr[L.p_rs + 3 * k + 1];
+            const double dx = pr[L.p_rs + 3 * k2] - ax, dy = pr[L.p_rs + 3 * k2 + 1] - ay;
+            S[L.o_seg + k] = ax;
+            S[L.o_seg + N + k] = ay;
+            S[L.o_seg + 2 * N + k] = dx;
+            S[L.o_seg + 3 * N + k] = dy;
+            S[L.o_seg + 4 * N + k] = 1.0 / (dx * dx + dy * dy + 1e-16);
+        }
+        for (int r = tid; r < L.Nother; r += nt) {
+            S[L.o_c0 + r] = pr[L.p_c0 + 3 * r];
+            S[L.o_c0 + L.Nother + r] = pr[L.p_c0 + 3 * r + 1];
+        }
+        for (int i = tid; i < L.Nother * N; i += nt) {   // i = r*N + k; c is robot-major
+            const int r = i / N, k = i - r * N;
+            S[L.o_c + i] = pr[L.p_c + r * 3 * N + 3 * k];
+            S[L.o_c + L.Nother * N + i] = pr[L.p_c + r * 3 * N + 3 * k + 1];
+        }
+        for (int i = tid; i < L.Nstc * L.nedge; i += nt) {
+            const int pl = i / L.nedge, e = i - pl * L.nedge;
+            const double* q = pr + L.p_os + pl * 3 * L.nedge;
+            S[L.o_poly + 3 * i] = q[e];
+            S[L.o_poly + 3 * i + 1] = -q[L.nedge + e];
+            S[L.o_poly + 3 * i + 2] = -q[2 * L.nedge + e];
+        }
+        for (int i = tid; i < L.Ndyn * (N + 1); i += nt) {   // i = obstacle*(N+1) + t
+            const int ob = i / (N + 1), t = i - ob * (N + 1);
+            const double* q = pr + L.p_od + (size_t)i * 6;
+            const double rx = q[2], ry = q[3];
+            const double rxi = t == 0 ? rx + P.vmargin + P.smargin : rx + P.vmargin;
+            const double ryi = t == 0 ? ry + P.vmargin + P.smargin : ry + P.vmargin;
+            const double wgt = t == 0 ? 1000.0 : pr[L.p_qdyn + t - 1];
+            double sa, ca;
+            sincos(q[4], &sa, &ca);
+            double f[EF];
+            f[E_CX] = q[0]; f[E_CY] = q[1]; f[E_CA] = ca; f[E_SA] = sa;
+            f[E_I1I] = 1.0 / ((rxi + 1e-6) * (rxi + 1e-6));
+            f[E_I2I] = 1.0 / ((ryi + 1e-6) * (ryi + 1e-6));
+            f[E_I1R] = 1.0 / ((rx + 1e-6) * (rx + 1e-6));
+            f[E_I2R] = 1.0 / ((ry + 1e-6) * (ry + 1e-6));
+            f[E_WAL] = wgt * q[5];
+#pragma unroll
+            for (int m = 0; m < EF; ++m) {
+                if (t == 0) S[L.o_e0 + m * L.Ndyn + ob] = f[m];
+                else S[L.o_et + (m * L.Ndyn + ob) * N + (t - 1)] = f[m];
+            }
+        }
+    }
+}
+
+// CTA-shared bookkeeping at the front of dynamic shared memory
+struct CtaShared {
+    uint64_t bar;
+    int work;
+    int pad;
+};
+
+// load the scenario blocks [sc0, sc1] into shared memory with TMA bulk copies
+__device__ __forceinline__ void load_scenarios(const KParams& P, const double* staged, double* dst,
+                                               int sc0, int sc1, uint64_t* bar, uint32_t& phase)
+{
+    const uint32_t blk = (uint32_t)P.L.total * 8u;
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, blk * (uint32_t)(sc1 - sc0 + 1));
+        for (int s = sc0; s <= sc1; ++s) {
+            const char* src = reinterpret_cast<const char*>(staged + (size_t)s * P.L.total);
+            char* d = reinterpret_cast<char*>(dst + (size_t)(s - sc0) * P.L.total);
+            for (uint32_t off = 0; off < blk; off += 32768u) {
+                const uint32_t n = blk - off < 32768u ? blk - off : 32768u;
+                tma_bulk_g2s(d + off, src + off, n, bar);
+            }
+        }
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+}
+
+// ---------------------------------------------------------------- K2: evaluation
+template <int SPL, bool SMEM>
+__global__ void __launch_bounds__(256) eval_kernel(const KParams P, const double* __restrict__ staged,
+                                                   const double* __restrict__ u,
+                                                   const double* __restrict__ y,
+                                                   const double* __restrict__ c, double* f,
+                                                   double* psi, double* grad, double* F1, double* F2)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CtaShared* cs = reinterpret_cast<CtaShared*>(smem_raw);
+    double* scn = reinterpret_cast<double*>(smem_raw + 16);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int N = P.L.N;
+    const int b0 = blockIdx.x * P.warps;
+    const int blast = min(b0 + P.warps, P.B) - 1;
+    const int sc0 = b0 / P.starts, sc1 = blast / P.starts;
+    uint32_t phase = 0;
+    if (SMEM) {
+        if (threadIdx.x == 0) {
+            mbar_init(&cs->bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        load_scenarios(P, staged, scn, sc0, sc1, &cs->bar, phase);
+    }
+    const int b = b0 + warp;
+    if (b >= P.B) return;
+    const int sc = b / P.starts;
+    const double* S = SMEM ? scn + (size_t)(sc - sc0) * P.L.total : staged + (size_t)sc * P.L.total;
+
+    double v[SPL], w[SPL], ya[SPL], yw[SPL];
+    bool act[SPL];
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+        const int k = lane + 32 * j;
+        act[j] = k < N;
+        v[j] = 0.0; w[j] = 0.0; ya[j] = 0.0; yw[j] = 0.0;
+        if (act[j]) {
+            v[j] = u[(size_t)b * 2 * N + 2 * k];
+            w[j] = u[(size_t)b * 2 * N + 2 * k + 1];
+            if (y) { ya[j] = y[(size_t)b * 2 * N + k]; yw[j] = y[(size_t)b * 2 * N + N + k]; }
+        }
+    }
+    const double cc = c ? c[b] : P.c_init;
+    const int n2 = P.L.Ndyn > 0 ? P.L.Ndyn : 1;
+    EvalOut<SPL> o;
+    eval_psi<SPL>(P, S, v, w, cc, ya, yw, true, o, lane, F2 ? F2 + (size_t)b * n2 : nullptr);
+    if (lane == 0) {
+        if (f) f[b] = o.f;
+        if (psi) psi[b] = o.psi;
+    }
+    // F1 = [acc; wacc]  (mpc_builder.py:158-160)
+    double vc = S[P.L.o_hdr + H_UM1V], wc = S[P.L.o_hdr + H_UM1W];
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+        const int k = lane + 32 * j;
+        double vp = __shfl_up_sync(FULL, v[j], 1), wp = __shfl_up_sync(FULL, w[j], 1);
+        if (lane == 0) { vp = vc; wp = wc; }
+        if (SPL > 1) { vc = __shfl_sync(FULL, v[j], 31); wc = __shfl_sync(FULL, w[j], 31); }
+        if (act[j]) {
+            if (grad) {
+                grad[(size_t)b * 2 * N + 2 * k] = o.gv[j];
+                grad[(size_t)b * 2 * N + 2 * k + 1] = o.gw[j];
+            }
+            if (F1) {
+                F1[(size_t)b * 2 * N + k] = (v[j] - vp) * P.inv_ts;
+                F1[(size_t)b * 2 * N + N + k] = (w[j] - wp) * P.inv_ts;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------- K1: solve
+template <int SPL, bool SMEM>
+__global__ void __launch_bounds__(256) solve_kernel(const KParams P, const double* __restrict__ staged,
+                                                    const SolveIO io, int* __restrict__ counter)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CtaShared* cs = reinterpret_cast<CtaShared*>(smem_raw);
+    double* scn = reinterpret_cast<double*>(smem_raw + 16);
+    double* lb_all = scn + (SMEM ? (size_t)P.nsc * P.L.total : 0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* lb = lb_all + (size_t)warp * P.lb_doubles;
+    const int ngroups = (P.B + P.warps - 1) / P.warps;
+    uint32_t phase = 0;
+    if (SMEM && threadIdx.x == 0) {
+        mbar_init(&cs->bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (;;) {
+        __syncthreads();   // previous group fully done with the scenario blocks / cs->work
+        if (threadIdx.x == 0) cs->work = atomicAdd(counter, 1);
+        __syncthreads();
+        const int g = cs->work;
+        if (g >= ngroups) break;
+        const int b0 = g * P.warps;
+        const int blast = min(b0 + P.warps, P.B) - 1;
+        const int sc0 = b0 / P.starts, sc1 = blast / P.starts;
+        if (SMEM) load_scenarios(P, staged, scn, sc0, sc1, &cs->bar, phase);
+        const int b = b0 + warp;
+        if (b < P.B) {
+            const int sc = b / P.starts;
+            const double* S = SMEM ? scn + (size_t)(sc - sc0) * P.L.total : staged + (size_t)sc * P.L.total;
+            solve_instance<SPL>(P, S, lb, b, lane, io);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ host side
+int build_layout(const mpcb_dims* d, Lay& L)
+{
+    if (!d) return MPCB_E_NULL;
+    if (d->N < 1 || d->N > MPCB_MAX_N || d->nedge < 1 || d->nedge > MPCB_MAX_EDGE || d->Nother < 0 ||
+        d->Nstc < 0 || d->Ndyn < 0)
+        return MPCB_E_DIMS;
+    const int N = d->N;
+    L.N = N; L.Nother = d->Nother; L.Nstc = d->Nstc; L.nedge = d->nedge; L.Ndyn = d->Ndyn;
+    int o = 0;
+    L.o_hdr = o;  o += H_SIZE;
+    L.o_rv = o;   o += N;
+    L.o_qstc = o; o += N;
+    L.o_seg = o;  o += 5 * N;
+    L.o_c0 = o;   o += 2 * d->Nother;
+    L.o_c = o;    o += 2 * d->Nother * N;
+    L.o_poly = o; o += 3 * d->nedge * d->Nstc;
+    L.o_e0 = o;   o += EF * d->Ndyn;
+    L.o_et = o;   o += EF * d->Ndyn * N;
+    L.total = (o + 1) & ~1;
+    int q = 0;
+    L.p_um1 = q; q += 2;
+    L.p_s0 = q;  q += 3;
+    L.p_sN = q;  q += 3;
+    L.p_q = q;   q += 10;
+    L.p_rs = q;  q += 3 * N;
+    L.p_rv = q;  q += N;
+    L.p_c0 = q;  q += 3 * d->Nother;
+    L.p_c = q;   q += 3 * N * d->Nother;
+    L.p_os = q;  q += 3 * d->nedge * d->Nstc;
+    L.p_od = q;  q += 6 * (N + 1) * d->Ndyn;
+    L.p_qstc = q; q += N;
+    L.p_qdyn = q; q += N;
+    L.np = q;
+    return MPCB_OK;
+}
+
+constexpr size_t WS_HEADER = 256;   // bytes reserved for the work-queue counter
+
+struct Plan {
+    KParams P;
+    bool smem;
+    int spl;
+    size_t smem_bytes;
+};
+
+int make_plan(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solver_cfg* c, int n_p, int starts,
+              bool need_lbfgs, Plan& pl)
+{
+    if (!d || !r || !c) return MPCB_E_NULL;
+    if (n_p < 1 || starts < 1) return MPCB_E_DIMS;
+    if (c->lbfgs_mem < 1 || c->lbfgs_mem > MPCB_MAX_LBFGS || c->max_inner < 1 || c->max_outer < 1)
+        return MPCB_E_DIMS;
+    KParams& P = pl.P;
+    memset(&P, 0, sizeof(P));
+    int rc = build_layout(d, P.L);
+    if (rc) return rc;
+    P.ts = r->ts; P.k6 = r->ts / 6.0; P.inv_ts = 1.0 / r->ts;
+    P.ds2 = r->vehicle_width * r->vehicle_width;
+    P.vmargin = r->vehicle_margin; P.smargin = r->social_margin;
+    P.vmin = r->lin_vel_min; P.vmax = r->lin_vel_max; P.wmax = r->ang_vel_max;
+    P.amin = r->lin_acc_min; P.amax = r->lin_acc_max; P.wamax = r->ang_acc_max;
+    P.tol = c->tolerance; P.tol0 = c->initial_tolerance; P.delta = c->delta_tolerance;
+    P.beta = c->inner_tol_update; P.rho = c->penalty_update; P.theta = c->sufficient_decrease;
+    P.c_init = c->initial_penalty; P.sy_eps = c->sy_epsilon; P.cb_eps = c->cbfgs_epsilon;
+    P.cb_alpha = c->cbfgs_alpha;
+    P.max_inner = c->max_inner; P.max_outer = c->max_outer; P.mem = c->lbfgs_mem;
+    P.n_p = n_p; P.starts = starts;
+    const long long B = (long long)n_p * starts;
+    if (B > 0x7fffffffLL / (2 * d->N)) return MPCB_E_DIMS;
+    P.B = (int)B;
+    pl.spl = d->N <= 32 ? 1 : 2;
+    const int M = c->lbfgs_mem + 1;
+    P.lb_doubles = need_lbfgs ? ((2 * M * 2 * d->N + 2 * M + 1) & ~1) : 0;
+
+    // choose warps per CTA so that the scenario blocks + per-warp L-BFGS fit in
+    // shared memory; fall back to reading the staged blocks from global (L1/L2)
+    const size_t cap = 227 * 1024;
+    const size_t blk = (size_t)P.L.total * 8, lbw = (size_t)P.lb_doubles * 8;
+    pl.smem = false;
+    int best_wps = 0;
+    for (int W = 8; W >= 1; W >>= 1) {
+        int nsc;
+        if (starts % W == 0) nsc = 1;
+        else if (W % starts == 0) nsc = W / starts;
+        else nsc = (W + starts - 2) / starts + 1;
+        const size_t need = 16 + nsc * blk + W * lbw;
+        if (need > cap) continue;
+        int ctas = (int)(cap / (need + 1024));   // + per-CTA reserved shared memory
+        if (ctas < 1) ctas = 1;
+        if (ctas * W > 32) ctas = 32 / W;
+        const int wps = ctas * W;                // resident warps per SM
+        if (wps > best_wps) {
+            best_wps = wps; pl.smem = true; P.warps = W; P.nsc = nsc; pl.smem_bytes = need;
+        }
+    }
+    if (best_wps < 8) {   // too few resident warps: read the staged blocks through L1/L2 instead
+        pl.smem = false;
+        P.warps = 8; P.nsc = 0;
+        pl.smem_bytes = 16 + 8 * lbw;
+    }
+    return MPCB_OK;
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes)
+{
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return MPCB_OK;
+}
+
+int stage(const Plan& pl, const double* p, void* workspace, size_t ws_bytes, cudaStream_t st,
+          double** staged_out, int** counter_out)
+{
+    const size_t need = WS_HEADER + (size_t)pl.P.n_p * pl.P.L.total * 8;
+    if (!workspace) return MPCB_E_NULL;
+    if (ws_bytes < need) return MPCB_E_WORKSPACE;
+    if ((reinterpret_cast<uintptr_t>(workspace) & 15) || (reinterpret_cast<uintptr_t>(p) & 7)) return MPCB_E_ALIGN;
+    int* counter = reinterpret_cast<int*>(workspace);
+    double* staged = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + WS_HEADER);
+    CUDA_TRY(cudaMemsetAsync(counter, 0, WS_HEADER, st));
+    const int grid = pl.P.n_p < 148 * 16 ? pl.P.n_p : 148 * 16;
+    stage_kernel<<<grid, 128, 0, st>>>(pl.P, p, staged);
+    CUDA_TRY(cudaGetLastError());
+    *staged_out = staged;
+    *counter_out = counter;
+    return MPCB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t mpcb_abi_version(void) { return MPCB_ABI_VERSION; }
+const char* mpcb_last_error(void) { return g_err; }
+
+int32_t mpcb_param_len(const mpcb_dims* d)
+{
+    Lay L;
+    return build_layout(d, L) ? -1 : L.np;
+}
+int32_t mpcb_num_decision(const mpcb_dims* d) { return d ? 2 * d->N : -1; }
+int32_t mpcb_n1(const mpcb_dims* d) { return d ? 2 * d->N : -1; }
+int32_t mpcb_n2(const mpcb_dims* d) { return d ? (d->Ndyn > 0 ? d->Ndyn : 1) : -1; }
+
+void mpcb_default_robot(mpcb_robot* r)
+{
+    if (!r) return;
+    r->ts = 0.2; r->vehicle_width = 0.5; r->vehicle_margin = 0.2; r->social_margin = 0.2;
+    r->lin_vel_min = -0.5; r->lin_vel_max = 1.5; r->ang_vel_max = 0.5;
+    r->lin_acc_min = -1.0; r->lin_acc_max = 1.0; r->ang_acc_max = 3.0;
+}
+void mpcb_default_solver_cfg(mpcb_solver_cfg* c)
+{
+    if (!c) return;
+    c->tolerance = 1e-4; c->initial_tolerance = 1e-4; c->delta_tolerance = 1e-4;
+    c->inner_tol_update = 0.1; c->penalty_update = 5.0; c->sufficient_decrease = 0.1;
+    c->initial_penalty = 10.0; c->sy_epsilon = 1e-10; c->cbfgs_epsilon = 1e-8; c->cbfgs_alpha = 1.0;
+    c->max_inner = 500; c->max_outer = 10; c->lbfgs_mem = 10; c->reserved = 0;
+}
+
+int32_t mpcb_workspace_bytes(const mpcb_dims* d, int32_t n_p, int32_t starts, size_t* bytes)
+{
+    Lay L;
+    int rc = build_layout(d, L);
+    if (rc) return rc;
+    if (!bytes) return MPCB_E_NULL;
+    if (n_p < 1 || starts < 1) return MPCB_E_DIMS;
+    *bytes = WS_HEADER + (size_t)n_p * L.total * 8;
+    return MPCB_OK;
+}
+
+int32_t mpcb_eval_f64(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solver_cfg* c, int32_t n_p,
+                      int32_t starts, const double* p, const double* u, const double* y,
+                      const double* cpen, double* f, double* psi, double* grad, double* F1, double* F2,
+                      void* workspace, size_t ws_bytes, void* stream)
+{
+    if (!p || !u) return MPCB_E_NULL;
+    Plan pl;
+    int rc = make_plan(d, r, c, n_p, starts, false, pl);
+    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    double* staged; int* counter;
+    rc = stage(pl, p, workspace, ws_bytes, st, &staged, &counter);
+    if (rc) return rc;
+    const int grid = (pl.P.B + pl.P.warps - 1) / pl.P.warps;
+    const int threads = pl.P.warps * 32;
+#define LAUNCH_EVAL(SPL, SM)                                                                       \
+    do {                                                                                           \
+        rc = set_smem(eval_kernel<SPL, SM>, pl.smem_bytes);                                        \
+        if (rc) return rc;                                                                         \
+        eval_kernel<SPL, SM><<<grid, threads, pl.smem_bytes, st>>>(pl.P, staged, u, y, cpen, f,    \
+                                                                    psi, grad, F1, F2);            \
+    } while (0)
+    if (pl.spl == 1) { if (pl.smem) LAUNCH_EVAL(1, true); else LAUNCH_EVAL(1, false); }
+    else             { if (pl.smem) LAUNCH_EVAL(2, true); else LAUNCH_EVAL(2, false); }
+#undef LAUNCH_EVAL
+    CUDA_TRY(cudaGetLastError());
+    return MPCB_OK;
+}
+
+int32_t mpcb_solve_f64(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solver_cfg* c, int32_t n_p,
+                       int32_t starts, const double* p, const double* u0, const double* y0,
+                       const double* c0, double* u_out, double* cost, int32_t* exit_status,
+                       int32_t* n_outer, int32_t* n_inner, double* fpr, double* f1_infeas,
+                       double* f2_norm, double* penalty, double* y_out, int32_t* evals,
+                       void* workspace, size_t ws_bytes, void* stream)
+{
+    if (!p || !u_out || !exit_status) return MPCB_E_NULL;
+    if ((reinterpret_cast<uintptr_t>(u_out) & 15) || (u0 && (reinterpret_cast<uintptr_t>(u0) & 15)))
+        return MPCB_E_ALIGN;
+    Plan pl;
+    int rc = make_plan(d, r, c, n_p, starts, true, pl);
+    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    double* staged; int* counter;
+    rc = stage(pl, p, workspace, ws_bytes, st, &staged, &counter);
+    if (rc) return rc;
+    SolveIO io{u0, y0, c0, u_out, cost, exit_status, n_outer, n_inner, fpr, f1_infeas, f2_norm, penalty, y_out, evals};
+    const int threads = pl.P.warps * 32;
+    const int ngroups = (pl.P.B + pl.P.warps - 1) / pl.P.warps;
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+#define LAUNCH_SOLVE(SPL, SM)                                                                      \
+    do {                                                                                           \
+        rc = set_smem(solve_kernel<SPL, SM>, pl.smem_bytes);                                       \
+        if (rc) return rc;                                                                         \
+        int per_sm = 0;                                                                            \
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_kernel<SPL, SM>,     \
+                                                               threads, pl.smem_bytes));           \
+        if (per_sm < 1) per_sm = 1;                                                                \
+        int grid = sms * per_sm;                                                                   \
+        if (grid > ngroups) grid = ngroups;                                                        \
+        solve_kernel<SPL, SM><<<grid, threads, pl.smem_bytes, st>>>(pl.P, staged, io, counter);    \
+    } while (0)
+    if (pl.spl == 1) { if (pl.smem) LAUNCH_SOLVE(1, true); else LAUNCH_SOLVE(1, false); }
+    else             { if (pl.smem) LAUNCH_SOLVE(2, true); else LAUNCH_SOLVE(2, false); }
+#undef LAUNCH_SOLVE
+    CUDA_TRY(cudaGetLastError());
+    return MPCB_OK;
+}
+
+int32_t mpcb_solve_one_host(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solver_cfg* c,
+                            const double* p_host, const double* u0_host, const double* y0_host,
+                            const double* c0_host, double* u_out_host, double* y_out_host,
+                            int32_t* exit_status_host, double* out_scalars)
+{
+    if (!p_host || !u_out_host || !exit_status_host) return MPCB_E_NULL;
+    Lay L;
+    int rc = build_layout(d, L);
+    if (rc) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        snprintf(g_err, sizeof(g_err), "no CUDA device");
+        return MPCB_E_NO_DEVICE;
+    }
+    const int n = 2 * d->N;
+    size_t ws = 0;
+    mpcb_workspace_bytes(d, 1, 1, &ws);
+    // one device arena: p | u0 | y0 | c0 | u | y | scalars(5 doubles) | ints(5) | workspace
+    const size_t o_p = 0, o_u0 = o_p + (size_t)L.np * 8, o_y0 = o_u0 + (size_t)n * 8,
+                 o_c0 = o_y0 + (size_t)n * 8, o_u = o_c0 + 16, o_y = o_u + (size_t)n * 8,
+                 o_sc = o_y + (size_t)n * 8, o_i = o_sc + 5 * 8, o_ws = (o_i + 5 * 4 + 255) & ~(size_t)255;
+    char* arena = nullptr;
+    CUDA_TRY(cudaMalloc(&arena, o_ws + ws));
+    cudaStream_t st = 0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaMemcpyAsync(arena + o_p, p_host, (size_t)L.np * 8, cudaMemcpyHostToDevice, st);
+    if (u0_host) cudaMemcpyAsync(arena + o_u0, u0_host, (size_t)n * 8, cudaMemcpyHostToDevice, st);
+    if (y0_host) cudaMemcpyAsync(arena + o_y0, y0_host, (size_t)n * 8, cudaMemcpyHostToDevice, st);
+    if (c0_host) cudaMemcpyAsync(arena + o_c0, c0_host, 8, cudaMemcpyHostToDevice, st);
+    double* sc = reinterpret_cast<double*>(arena + o_sc);
+    int32_t* iv = reinterpret_cast<int32_t*>(arena + o_i);
+    cudaEventRecord(e0, st);
+    rc = mpcb_solve_f64(d, r, c, 1, 1, reinterpret_cast<double*>(arena + o_p),
+                        u0_host ? reinterpret_cast<double*>(arena + o_u0) : nullptr,
+                        y0_host ? reinterpret_cast<double*>(arena + o_y0) : nullptr,
+                        c0_host ? reinterpret_cast<double*>(arena + o_c0) : nullptr,
+                        reinterpret_cast<double*>(arena + o_u), sc + 0, iv + 0, iv + 1, iv + 2, sc + 1,
+                        sc + 2, sc + 3, sc + 4, reinterpret_cast<double*>(arena + o_y), iv + 3,
+                        arena + o_ws, ws, st);
+    cudaEventRecord(e1, st);
+    double hsc[5]; int32_t hiv[5];
+    if (rc == MPCB_OK) {
+        cudaMemcpyAsync(u_out_host, arena + o_u, (size_t)n * 8, cudaMemcpyDeviceToHost, st);
+        if (y_out_host) cudaMemcpyAsync(y_out_host, arena + o_y, (size_t)n * 8, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(hsc, sc, sizeof(hsc), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(hiv, iv, sizeof(hiv), cudaMemcpyDeviceToHost, st);
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(arena);
+    if (rc) return rc;
+    if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "solve: %s", cudaGetErrorString(e));
+        return MPCB_E_CUDA;
+    }
+    *exit_status_host = hiv[0];
+    if (out_scalars) {
+        out_scalars[0] = hsc[0]; out_scalars[1] = hsc[1]; out_scalars[2] = hsc[2];
+        out_scalars[3] = hsc[3]; out_scalars[4] = hsc[4];
+        out_scalars[5] = hiv[1]; out_scalars[6] = hiv[2]; out_scalars[7] = ms;
+    }
+    return MPCB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,493 @@
+// mpcb_solver.cuh — warp-resident PANOC + ALM/PM for one instance.
+// Restates OpEn's optimization_engine (PANOCEngine::init/step,
+// PANOCOptimizer::solve, AlmOptimizer::step/solve) and the lbfgs crate's
+// update_hessian/apply_hessian; the reference configures them in
+// mpc_builder.py:171-198.  oracle/mpc_oracle.c holds the CPU restatement this
+// code is checked against, routine by routine.
+#pragma once
+#include "mpcb_device.cuh"
+#include "../../include/mpcb.h"
+
+namespace mpcb {
+
+// L-BFGS memory of one warp, in shared memory: rows [M][2N] of s and y (lane k
+// touches elements k and N+k of a row: conflict-free), rho[M], alpha[M].
+template <int SPL>
+struct Lbfgs {
+    double* s;      // [M][2N]
+    double* y;      // [M][2N]
+    double* rho;    // [M]
+    double* alpha;  // [M]
+    int M, N, mem;
+    int head;       // physical row of logical slot 0
+    int active;
+    bool first_old;
+    double gamma;
+    double os0[SPL], os1[SPL], og0[SPL], og1[SPL];   // old_state, old_g (registers)
+
+    __device__ __forceinline__ void bind(double* base, int N_, int mem_)
+    {
+        N = N_; mem = mem_; M = mem_ + 1;
+        s = base;
+        y = s + M * 2 * N;
+        rho = y + M * 2 * N;
+        alpha = rho + M;
+        head = 0; active = 0; first_old = true; gamma = 1.0;
+    }
+    __device__ __forceinline__ void reset() { active = 0; first_old = true; }
+    __device__ __forceinline__ int phys(int logical) const
+    {
+        int r = head + logical;
+        return r >= M ? r - M : r;
+    }
+};
+
+template <int SPL>
+struct Inst {   // per-lane slice of the solver state of one instance
+    double u0[SPL], u1[SPL];       // iterate (v_k, w_k)
+    double g0[SPL], g1[SPL];       // gradient_u
+    double gp0[SPL], gp1[SPL];     // gradient_u_previous
+    double h0[SPL], h1[SPL];       // u_half_step
+    double r0[SPL], r1[SPL];       // gamma_fpr
+    double d0[SPL], d1[SPL];       // direction_lbfgs
+    double s0[SPL], s1[SPL];       // gradient_step
+    double ya[SPL], yw[SPL];       // Lagrange multipliers of (acc_k, wacc_k)
+    double c;                      // penalty
+    double gamma, sigma, Lc, cost, norm_r, akkt_tol;
+    int iter;
+    int n_cost, n_grad;
+};
+
+#define MPCB_FORJ _Pragma("unroll") for (int j = 0; j < SPL; ++j)
+
+template <int SPL>
+__device__ __forceinline__ double sumsq2(const double (&a)[SPL], const double (&b)[SPL])
+{
+    double s = 0.0;
+    MPCB_FORJ s = fma(a[j], a[j], fma(b[j], b[j], s));
+    return warp_sum(s);
+}
+
+template <int SPL>
+__device__ __forceinline__ void project_U(const KParams& P, const double (&a0)[SPL],
+                                          const double (&a1)[SPL], double (&o0)[SPL],
+                                          double (&o1)[SPL])
+{
+    MPCB_FORJ {
+        o0[j] = a0[j] < P.vmin ? P.vmin : (a0[j] > P.vmax ? P.vmax : a0[j]);
+        o1[j] = a1[j] < -P.wmax ? -P.wmax : (a1[j] > P.wmax ? P.wmax : a1[j]);
+    }
+}
+
+template <int SPL>
+__device__ __forceinline__ void grad_and_half_step(const KParams& P, Inst<SPL>& I,
+                                                   const double (&p0)[SPL], const double (&p1)[SPL])
+{
+    MPCB_FORJ {
+        I.s0[j] = fma(-I.gamma, I.g0[j], p0[j]);
+        I.s1[j] = fma(-I.gamma, I.g1[j], p1[j]);
+    }
+    project_U<SPL>(P, I.s0, I.s1, I.h0, I.h1);
+}
+
+// lbfgs crate: update_hessian(g = gamma_fpr, s = u)
+template <int SPL>
+__device__ __forceinline__ void lbfgs_update(const KParams& P, Lbfgs<SPL>& B, const Inst<SPL>& I,
+                                             int lane, const bool (&act)[SPL])
+{
+    if (B.first_old) {
+        B.first_old = false;
+        MPCB_FORJ { B.os0[j] = I.u0[j]; B.os1[j] = I.u1[j]; B.og0[j] = I.r0[j]; B.og1[j] = I.r1[j]; }
+        return;
+    }
+    double sn0[SPL], sn1[SPL], yn0[SPL], yn1[SPL];
+    double ys = 0.0, ss = 0.0, yy = 0.0;
+    MPCB_FORJ {
+        sn0[j] = I.u0[j] - B.os0[j]; sn1[j] = I.u1[j] - B.os1[j];
+        yn0[j] = I.r0[j] - B.og0[j]; yn1[j] = I.r1[j] - B.og1[j];
+        ys = fma(sn0[j], yn0[j], fma(sn1[j], yn1[j], ys));
+        ss = fma(sn0[j], sn0[j], fma(sn1[j], sn1[j], ss));
+        yy = fma(yn0[j], yn0[j], fma(yn1[j], yn1[j], yy));
+    }
+    ys = warp_sum(ys); ss = warp_sum(ss); yy = warp_sum(yy);
+    bool ok;
+    if (ss <= 2.2250738585072014e-308 || (P.sy_eps > 0.0 && ys <= P.sy_eps)) {
+        ok = false;
+    } else if (P.cb_eps > 0.0 && P.cb_alpha > 0.0) {
+        const double lhs = ys / ss;
+        const double rhs = P.cb_eps * (P.cb_alpha == 1.0 ? I.norm_r : pow(I.norm_r, P.cb_alpha));
+        ok = lhs > rhs && isfinite(lhs) && isfinite(rhs);
+    } else {
+        ok = true;
+    }
+    if (!ok) return;
+    MPCB_FORJ { B.os0[j] = I.u0[j]; B.os1[j] = I.u1[j]; B.og0[j] = I.r0[j]; B.og1[j] = I.r1[j]; }
+    // rotate_right(1): the scratch row (logical M-1) becomes logical 0
+    B.head = B.head == 0 ? B.M - 1 : B.head - 1;
+    double* sr = B.s + B.head * 2 * B.N;
+    double* yr = B.y + B.head * 2 * B.N;
+    MPCB_FORJ {
+        if (act[j]) {
+            const int k = lane + 32 * j;
+            sr[k] = sn0[j]; sr[B.N + k] = sn1[j];
+            yr[k] = yn0[j]; yr[B.N + k] = yn1[j];
+        }
+    }
+    if (lane == 0) B.rho[B.head] = 1.0 / ys;
+    B.gamma = ys / yy;
+    B.active = B.active + 1 < B.mem ? B.active + 1 : B.mem;
+    __syncwarp();
+}
+
+// lbfgs crate: apply_hessian (two-loop recursion) on q = (d0, d1)
+template <int SPL>
+__device__ __forceinline__ void lbfgs_apply(Lbfgs<SPL>& B, double (&q0)[SPL], double (&q1)[SPL],
+                                            int lane, const bool (&act)[SPL])
+{
+    if (B.active == 0) return;
+    for (int k = 0; k < B.active; ++k) {
+        const int row = B.phys(k);
+        const double* sr = B.s + row * 2 * B.N;
+        const double* yr = B.y + row * 2 * B.N;
+        double sv0[SPL], sv1[SPL], yv0[SPL], yv1[SPL], part = 0.0;
+        MPCB_FORJ {
+            const int kk = act[j] ? lane + 32 * j : 0;
+            sv0[j] = act[j] ? sr[kk] : 0.0; sv1[j] = act[j] ? sr[B.N + kk] : 0.0;
+            yv0[j] = act[j] ? yr[kk] : 0.0; yv1[j] = act[j] ? yr[B.N + kk] : 0.0;
+            part = fma(sv0[j], q0[j], fma(sv1[j], q1[j], part));
+        }
+        const double a = B.rho[row] * warp_sum(part);
+        if (lane == 0) B.alpha[row] = a;
+        MPCB_FORJ { q0[j] = fma(-a, yv0[j], q0[j]); q1[j] = fma(-a, yv1[j], q1[j]); }
+    }
+    __syncwarp();
+    MPCB_FORJ { q0[j] *= B.gamma; q1[j] *= B.gamma; }
+    for (int k = B.active - 1; k >= 0; --k) {
+        const int row = B.phys(k);
+        const double* sr = B.s + row * 2 * B.N;
+        const double* yr = B.y + row * 2 * B.N;
+        double sv0[SPL], sv1[SPL], part = 0.0;
+        MPCB_FORJ {
+            const int kk = act[j] ? lane + 32 * j : 0;
+            sv0[j] = act[j] ? sr[kk] : 0.0; sv1[j] = act[j] ? sr[B.N + kk] : 0.0;
+            const double y0 = act[j] ? yr[kk] : 0.0, y1 = act[j] ? yr[B.N + kk] : 0.0;
+            part = fma(y0, q0[j], fma(y1, q1[j], part));
+        }
+        const double beta = B.rho[row] * warp_sum(part);
+        const double cf = B.alpha[row] - beta;
+        MPCB_FORJ { q0[j] = fma(cf, sv0[j], q0[j]); q1[j] = fma(cf, sv1[j], q1[j]); }
+    }
+}
+
+template <int SPL>
+__device__ __forceinline__ void compute_fpr(Inst<SPL>& I)
+{
+    MPCB_FORJ { I.r0[j] = I.u0[j] - I.h0[j]; I.r1[j] = I.u1[j] - I.h1[j]; }
+    I.norm_r = sqrt(sumsq2<SPL>(I.r0, I.r1));
+}
+
+struct SolveIO {
+    const double* u0; const double* y0; const double* c0;
+    double* u_out; double* cost; int32_t* exit_status; int32_t* n_outer; int32_t* n_inner;
+    double* fpr; double* f1_infeas; double* f2_norm; double* penalty; double* y_out; int32_t* evals;
+};
+
+// What the pending horizon evaluation is for.  The whole ALM/PANOC run is one
+// loop around a single inlined eval_psi call site (small code footprint, no
+// solver state in local memory): every handler ends by choosing the next point
+// to evaluate.
+enum EvalFor { ST_INIT, ST_INIT_LIP, ST_LIP_HALF, ST_LIP_U0, ST_LIP_LOOP, ST_NOLS, ST_LS, ST_ALM };
+
+// AlmOptimizer::solve + PANOCOptimizer::solve + PANOCEngine::{init,step} for instance b.
+template <int SPL>
+__device__ __forceinline__ void solve_instance(const KParams& P, const double* __restrict__ S,
+                                               double* lb_mem, int b, int lane, const SolveIO& io)
+{
+    const int N = P.L.N;
+    bool act[SPL];
+    MPCB_FORJ act[j] = lane + 32 * j < N;
+    Inst<SPL> I;
+    Lbfgs<SPL> B;
+    B.bind(lb_mem, N, P.mem);
+    I.n_cost = 0; I.n_grad = 0;
+    MPCB_FORJ {
+        const int k = lane + 32 * j;
+        I.u0[j] = 0.0; I.u1[j] = 0.0; I.ya[j] = 0.0; I.yw[j] = 0.0;
+        I.gp0[j] = 0.0; I.gp1[j] = 0.0; I.g0[j] = 0.0; I.g1[j] = 0.0;
+        I.h0[j] = 0.0; I.h1[j] = 0.0; I.r0[j] = 0.0; I.r1[j] = 0.0;
+        I.d0[j] = 0.0; I.d1[j] = 0.0; I.s0[j] = 0.0; I.s1[j] = 0.0;
+        if (act[j]) {
+            if (io.u0) {
+                const double2 t = reinterpret_cast<const double2*>(io.u0 + (size_t)b * 2 * N)[k];
+                I.u0[j] = t.x; I.u1[j] = t.y;
+            }
+            if (io.y0) {
+                I.ya[j] = io.y0[(size_t)b * 2 * N + k];
+                I.yw[j] = io.y0[(size_t)b * 2 * N + N + k];
+            }
+        }
+    }
+    I.c = io.c0 ? io.c0[b] : P.c_init;
+    I.akkt_tol = P.tol0;
+    I.gamma = 0.0; I.sigma = 0.0; I.Lc = 0.0; I.cost = 0.0; I.norm_r = 0.0; I.iter = 0;
+
+    double yp_a[SPL], yp_w[SPL];
+    double pt0[SPL], pt1[SPL];          // the point of the pending evaluation
+    MPCB_FORJ { yp_a[j] = 0.0; yp_w[j] = 0.0; pt0[j] = 0.0; pt1[j] = 0.0; }
+    double dy = 0.0, dy_plus = 0.0, f2n = 0.0, f2n_plus = 0.0, last_fpr = -1.0, fcost = 0.0;
+    double cost_half = 0.0, rhs_ls = 0.0, tau = 1.0, ceff = 0.0;
+    int alm_iter = 0, n_outer = 0, inner_total = 0, outer = 1;
+    int num_iter = 0, it_lip = 0, ls = 0, inner = MPCB_CONVERGED;
+    int status = MPCB_CONVERGED;
+    int st = ST_INIT;
+    bool cont = true, flag = true, want_grad = true, failed = false;
+    const double EPS = 2.220446049250313e-16;
+    EvalOut<SPL> o;
+
+L_outer_begin:   // ---- AlmOptimizer::step: project y on Y, then the inner problem
+    ++n_outer;
+    MPCB_FORJ {
+        I.ya[j] = fmin(fmax(I.ya[j], -1e12), 1e12);
+        I.yw[j] = fmin(fmax(I.yw[j], -1e12), 1e12);
+        I.gp0[j] = 0.0; I.gp1[j] = 0.0;   // set_akkt_tolerance zeroes the cached previous gradient
+    }
+    // PANOCEngine::init
+    B.reset();
+    I.iter = 0; num_iter = 0; cont = true;
+    MPCB_FORJ { pt0[j] = I.u0[j]; pt1[j] = I.u1[j]; }
+    want_grad = true; ceff = I.c; st = ST_INIT;
+
+L_eval:
+    eval_psi<SPL>(P, S, pt0, pt1, ceff, I.ya, I.yw, want_grad, o, lane);
+    if (want_grad) I.n_grad++; else I.n_cost++;
+    switch (st) {
+        case ST_INIT: goto H_INIT;
+        case ST_INIT_LIP: goto H_INIT_LIP;
+        case ST_LIP_HALF: goto H_LIP_HALF;
+        case ST_LIP_U0: goto H_LIP_U0;
+        case ST_LIP_LOOP: goto H_LIP_LOOP;
+        case ST_NOLS: goto H_NOLS;
+        case ST_LS: goto H_LS;
+        default: goto H_ALM;
+    }
+
+H_INIT: {   // cost and gradient at u; then perturb for the Lipschitz estimate
+    I.cost = o.psi;
+    double hs = 0.0;
+    MPCB_FORJ {
+        I.g0[j] = o.gv[j]; I.g1[j] = o.gw[j];
+        // LipschitzEstimator: h = max(1e-6*u, 1e-12); u stays perturbed, as upstream
+        const double h0 = act[j] ? ((1e-6 * I.u0[j] > 1e-12) ? 1e-6 * I.u0[j] : 1e-12) : 0.0;
+        const double h1 = act[j] ? ((1e-6 * I.u1[j] > 1e-12) ? 1e-6 * I.u1[j] : 1e-12) : 0.0;
+        hs = fma(h0, h0, fma(h1, h1, hs));
+        I.u0[j] += h0; I.u1[j] += h1;
+        pt0[j] = I.u0[j]; pt1[j] = I.u1[j];
+    }
+    I.norm_r = sqrt(warp_sum(hs));   // |h| parked here until H_INIT_LIP
+    st = ST_INIT_LIP;
+    goto L_eval;
+}
+H_INIT_LIP: {
+    double t0[SPL], t1[SPL];
+    MPCB_FORJ { t0[j] = o.gv[j] - I.g0[j]; t1[j] = o.gw[j] - I.g1[j]; }
+    I.Lc = sqrt(sumsq2<SPL>(t0, t1)) / I.norm_r;
+    I.gamma = 0.95 / fmax(I.Lc, 1e-10);
+    I.sigma = (1.0 - 0.95) / (4.0 * I.gamma);
+    grad_and_half_step<SPL>(P, I, I.u0, I.u1);
+    goto L_step_begin;
+}
+
+L_step_begin:   // ---- PANOCEngine::step
+    if (I.iter >= 1) { MPCB_FORJ { I.gp0[j] = I.g0[j]; I.gp1[j] = I.g1[j]; } }
+    compute_fpr<SPL>(I);
+    if (I.norm_r < P.tol) {
+        double a = 0.0;
+        MPCB_FORJ {
+            const double t0 = I.r0[j] / I.gamma + I.g0[j] - I.gp0[j];
+            const double t1 = I.r1[j] / I.gamma + I.g1[j] - I.gp1[j];
+            a = fma(t0, t0, fma(t1, t1, a));
+        }
+        if (sqrt(warp_sum(a)) < I.akkt_tol) { flag = false; goto L_step_return; }
+    }
+    // update_lipschitz_constant: cost at the half step first
+    MPCB_FORJ { pt0[j] = I.h0[j]; pt1[j] = I.h1[j]; }
+    want_grad = false; st = ST_LIP_HALF;
+    goto L_eval;
+
+H_LIP_HALF:
+    cost_half = o.psi;
+    it_lip = 0;
+    if (I.iter == 0) {   // cost at the (perturbed) start point; later iterations already hold it
+        MPCB_FORJ { pt0[j] = I.u0[j]; pt1[j] = I.u1[j]; }
+        st = ST_LIP_U0;
+        goto L_eval;
+    }
+    goto L_lip_check;
+H_LIP_U0:
+    I.cost = o.psi;
+    goto L_lip_check;
+H_LIP_LOOP:
+    cost_half = o.psi;
+    compute_fpr<SPL>(I);
+    ++it_lip;
+    goto L_lip_check;
+
+L_lip_check: {
+    const double ip = dotw<SPL>(I.g0, I.g1, I.r0, I.r1);
+    const double rhs = I.cost + 1e-6 * fabs(I.cost) - ip + (0.95 / (2.0 * I.gamma)) * (I.norm_r * I.norm_r);
+    if (cost_half > rhs && it_lip < 10 && I.Lc < 1e9) {
+        B.reset();
+        I.Lc *= 2.0;
+        I.gamma /= 2.0;
+        grad_and_half_step<SPL>(P, I, I.u0, I.u1);
+        MPCB_FORJ { pt0[j] = I.h0[j]; pt1[j] = I.h1[j]; }
+        st = ST_LIP_LOOP;
+        goto L_eval;
+    }
+    I.sigma = (1.0 - 0.95) / (4.0 * I.gamma);
+    // lbfgs_direction
+    lbfgs_update<SPL>(P, B, I, lane, act);
+    if (I.iter > 0) {
+        MPCB_FORJ { I.d0[j] = I.r0[j]; I.d1[j] = I.r1[j]; }
+        lbfgs_apply<SPL>(B, I.d0, I.d1, lane, act);
+    }
+    want_grad = true;
+    if (I.iter == 0) {   // update_no_linesearch
+        MPCB_FORJ { I.u0[j] = I.h0[j]; I.u1[j] = I.h1[j]; pt0[j] = I.u0[j]; pt1[j] = I.u1[j]; }
+        st = ST_NOLS;
+        goto L_eval;
+    }
+    // linesearch on the forward-backward envelope
+    double dd = 0.0;
+    MPCB_FORJ {
+        const double e0 = I.s0[j] - I.h0[j], e1 = I.s1[j] - I.h1[j];
+        dd = fma(e0, e0, fma(e1, e1, dd));
+    }
+    const double dist2 = warp_sum(dd);
+    const double fbe = I.cost - 0.5 * I.gamma * sumsq2<SPL>(I.g0, I.g1) + 0.5 * dist2 / I.gamma;
+    rhs_ls = fbe - I.sigma * (I.norm_r * I.norm_r);
+    tau = 1.0;
+    ls = 0;
+    MPCB_FORJ {
+        pt0[j] = I.u0[j] - (1.0 - tau) * I.r0[j] - tau * I.d0[j];
+        pt1[j] = I.u1[j] - (1.0 - tau) * I.r1[j] - tau * I.d1[j];
+    }
+    st = ST_LS;
+    goto L_eval;
+}
+H_NOLS:
+    I.cost = o.psi;
+    MPCB_FORJ { I.g0[j] = o.gv[j]; I.g1[j] = o.gw[j]; }
+    grad_and_half_step<SPL>(P, I, I.u0, I.u1);
+    I.iter++;
+    flag = true;
+    goto L_step_return;
+H_LS: {
+    I.cost = o.psi;
+    MPCB_FORJ { I.g0[j] = o.gv[j]; I.g1[j] = o.gw[j]; }
+    grad_and_half_step<SPL>(P, I, pt0, pt1);
+    double d2 = 0.0;
+    MPCB_FORJ {
+        const double e0 = I.s0[j] - I.h0[j], e1 = I.s1[j] - I.h1[j];
+        d2 = fma(e0, e0, fma(e1, e1, d2));
+    }
+    d2 = warp_sum(d2);
+    const double lhs = I.cost - 0.5 * I.gamma * sumsq2<SPL>(I.g0, I.g1) + 0.5 * d2 / I.gamma;
+    if (lhs > rhs_ls && ls < 10) {
+        tau /= 2.0;
+        ++ls;
+        MPCB_FORJ {
+            pt0[j] = I.u0[j] - (1.0 - tau) * I.r0[j] - tau * I.d0[j];
+            pt1[j] = I.u1[j] - (1.0 - tau) * I.r1[j] - tau * I.d1[j];
+        }
+        goto L_eval;
+    }
+    // upstream keeps the last trial point even when the search is exhausted
+    MPCB_FORJ { I.u0[j] = pt0[j]; I.u1[j] = pt1[j]; }
+    I.iter++;
+    flag = true;
+    goto L_step_return;
+}
+
+L_step_return:   // PANOCOptimizer::solve: flag = step(); while (flag && cont) { ... step() }
+    if (flag && cont) {
+        ++num_iter;
+        cont = num_iter < P.max_inner;
+        goto L_step_begin;
+    }
+    {
+        bool fin = true;
+        MPCB_FORJ fin = fin && isfinite(I.u0[j]) && isfinite(I.u1[j]);
+        if (!__all_sync(FULL, fin)) { status = MPCB_NOT_FINITE_COMPUTATION; failed = true; goto L_finish; }
+    }
+    MPCB_FORJ { I.u0[j] = I.h0[j]; I.u1[j] = I.h1[j]; }   // return u_bar (always feasible)
+    inner = cont ? MPCB_CONVERGED : MPCB_NOT_CONVERGED_ITERATIONS;
+    last_fpr = I.norm_r;
+    inner_total += num_iter;
+    // F1(u), F2(u), f(u) at the inner solution: one horizon evaluation with c = 0
+    MPCB_FORJ { pt0[j] = I.u0[j]; pt1[j] = I.u1[j]; }
+    want_grad = false; ceff = 0.0; st = ST_ALM;
+    goto L_eval;
+
+H_ALM: {
+    fcost = o.f;
+    f2n_plus = sqrt(o.f2sq);
+    // update_lagrange_multipliers: y+ = y + c (F1 - Proj_C(F1 + y/c))
+    double dsum = 0.0;
+    double vc = S[P.L.o_hdr + H_UM1V], wc = S[P.L.o_hdr + H_UM1W];
+    MPCB_FORJ {
+        double vp = __shfl_up_sync(FULL, I.u0[j], 1), wp = __shfl_up_sync(FULL, I.u1[j], 1);
+        if (lane == 0) { vp = vc; wp = wc; }
+        if (SPL > 1) { vc = __shfl_sync(FULL, I.u0[j], 31); wc = __shfl_sync(FULL, I.u1[j], 31); }
+        const double acc = (I.u0[j] - vp) * P.inv_ts, wacc = (I.u1[j] - wp) * P.inv_ts;
+        const double za = acc + I.ya[j] / I.c, zw = wacc + I.yw[j] / I.c;
+        const double pa = fmin(fmax(za, P.amin), P.amax), pw = fmin(fmax(zw, -P.wamax), P.wamax);
+        yp_a[j] = act[j] ? I.ya[j] + I.c * (acc - pa) : 0.0;
+        yp_w[j] = act[j] ? I.yw[j] + I.c * (wacc - pw) : 0.0;
+        const double e0 = yp_a[j] - I.ya[j], e1 = yp_w[j] - I.yw[j];
+        dsum = fma(e0, e0, fma(e1, e1, dsum));
+    }
+    dy_plus = sqrt(warp_sum(dsum));
+    // is_exit_criterion_satisfied
+    const bool c1 = alm_iter > 0 && dy_plus <= I.c * P.delta + EPS;
+    const bool c2 = f2n_plus <= P.delta + EPS;
+    const bool c3 = I.akkt_tol <= P.tol + EPS;
+    if (c1 && c2 && c3) { status = inner; goto L_finish; }
+    // is_penalty_stall_criterion
+    const bool stall = alm_iter == 0 || (dy_plus <= P.theta * dy + EPS && f2n_plus <= P.theta * f2n + EPS);
+    if (!stall) I.c *= P.rho;
+    I.akkt_tol = fmax(I.akkt_tol * P.beta, P.tol);
+    ++alm_iter;
+    dy = dy_plus;
+    f2n = f2n_plus;
+    MPCB_FORJ { I.ya[j] = yp_a[j]; I.yw[j] = yp_w[j]; }
+    if (outer < P.max_outer) { ++outer; goto L_outer_begin; }
+    goto L_finish;
+}
+
+L_finish:
+    if (!failed && n_outer == P.max_outer) status = MPCB_NOT_CONVERGED_ITERATIONS;
+    MPCB_FORJ {
+        const int k = lane + 32 * j;
+        if (act[j]) {
+            reinterpret_cast<double2*>(io.u_out + (size_t)b * 2 * N)[k] = make_double2(I.u0[j], I.u1[j]);
+            if (io.y_out) {
+                io.y_out[(size_t)b * 2 * N + k] = yp_a[j];
+                io.y_out[(size_t)b * 2 * N + N + k] = yp_w[j];
+            }
+        }
+    }
+    if (lane == 0) {
+        io.exit_status[b] = status;
+        if (io.cost) io.cost[b] = failed ? __longlong_as_double(0x7ff8000000000000LL) : fcost;
+        if (io.n_outer) io.n_outer[b] = n_outer;
+        if (io.n_inner) io.n_inner[b] = inner_total;
+        if (io.fpr) io.fpr[b] = last_fpr;
+        if (io.f1_infeas) io.f1_infeas[b] = dy_plus / I.c;
+        if (io.f2_norm) io.f2_norm[b] = f2n_plus;
+        if (io.penalty) io.penalty[b] = I.c;
+        if (io.evals) { io.evals[2 * b] = I.n_cost; io.evals[2 * b + 1] = I.n_grad; }
+    }
+}
+
+}  // namespace mpcb

@@ -13,7 +13,7 @@
  * points are DEVICE pointers (e.g. torch.Tensor.data_ptr()) unless the name
  * ends in `_host`.  Every function returns 0 on success or a negative
  * MPCB_E_* code; nothing throws, nothing allocates behind the caller's back
- * except the *_host convenience path, and all device work is ordered on the
+ * (the caller provides `workspace`) except the *_host convenience path, and all device work is ordered on the
  * `stream` argument (a cudaStream_t passed as void*).
  */
 #ifndef MPCB_H
@@ -111,6 +111,14 @@ void mpcb_default_robot(mpcb_robot* r);
 void mpcb_default_solver_cfg(mpcb_solver_cfg* c);
 
 /*
+ * Device workspace (bytes) the eval/solve entry points need for n_p parameter
+ * rows: the staged structure-of-arrays copy of every row (K3 writes it, the
+ * solve kernel TMA-loads it) plus the persistent work-queue counter.
+ */
+int32_t mpcb_workspace_bytes(const mpcb_dims* dims, int32_t n_p, int32_t starts,
+                             size_t* bytes);
+
+/*
  * Evaluate the augmented cost the inner solver minimises and its pieces, for
  * B instances:  psi(u; c, y) = f(u) + c/2 [ dist^2_C(F1(u)+y/max(c,1)) + |F2(u)|^2 ].
  * Replaces the CasADi-generated `cost`, `grad`, `mapping_f1`, `mapping_f2`
@@ -127,6 +135,7 @@ int32_t mpcb_eval_f64(const mpcb_dims* dims, const mpcb_robot* robot,
                       const double* y, const double* c,
                       double* f, double* psi, double* grad,
                       double* F1, double* F2,
+                      void* workspace, size_t workspace_bytes,
                       void* stream);
 
 /*
@@ -151,6 +160,7 @@ int32_t mpcb_solve_f64(const mpcb_dims* dims, const mpcb_robot* robot,
                        int32_t* n_outer, int32_t* n_inner,
                        double* fpr, double* f1_infeas, double* f2_norm,
                        double* penalty, double* y_out, int32_t* evals,
+                       void* workspace, size_t workspace_bytes,
                        void* stream);
 
 /*
