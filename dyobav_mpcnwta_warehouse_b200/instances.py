@@ -143,6 +143,14 @@ def generate(dims: Dims, n: int, seed: int, cfg: MpcConfig | None = None,
         a0[..., 0] = 2.0 / w;  a0[..., 1] = -2.0 / w
         a1[..., 2] = 2.0 / h;  a1[..., 3] = -2.0 / h
         b[...] = a0 * ctr[..., 0:1] + a1 * ctr[..., 1:2] + 1.0
+        # a rectangle placed next to one leg may cover another leg after a turn: drop every
+        # rectangle whose (0.3 m grown) interior contains the start or a reference sample —
+        # the map's obstacles never cover the planned path (unused polygon slots are zero rows)
+        chk = np.concatenate([state[:, None, :2], ref_pts], axis=1)                   # [n,N+1,2]
+        inx = np.abs(chk[:, None, :, 0] - ctr[:, :, None, 0]) < (w / 2 + 0.3)[:, :, None]
+        iny = np.abs(chk[:, None, :, 1] - ctr[:, :, None, 1]) < (h / 2 + 0.3)[:, :, None]
+        covered = (inx & iny).any(-1)                                                # [n,K]
+        b[covered] = 0.0; a0[covered] = 0.0; a1[covered] = 0.0
         o, ln = lay["o_s"]
         P[:, o:o + ln] = np.concatenate([b, a0, a1], axis=-1).reshape(n, -1)
 
