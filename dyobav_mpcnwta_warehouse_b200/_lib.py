@@ -8,7 +8,7 @@ import os
 from .problem import CDims, CRobot, CSolverCfg
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmpcb.so")
+LIB_PATH = os.environ.get("MPCB_LIB_PATH") or os.path.join(_HERE, "csrc", "libmpcb.so")
 _lib = None
 
 ERRORS = {-1: "unsupported or inconsistent dimensions", -2: "required pointer is NULL",

@@ -17,10 +17,14 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include "mpcb_device.cuh"
 #include "mpcb_solver.cuh"
 
+#ifndef MPCB_MIN_CTAS
+#define MPCB_MIN_CTAS 1
+#endif
 using namespace mpcb;
 
 namespace {
@@ -76,6 +80,14 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
 }
 
 // ------------------------------------------------------------------ K3: staging
+__device__ __forceinline__ double hypot_plain(double a, double b) { return sqrt(a * a + b * b); }
+// conservative float margin: dist - R, shrunk by 1e-9 relative + absolute, rounded down
+__device__ __forceinline__ float margin_f(double dist, double R)
+{
+    const double m = dist - R * (1.0 + 1e-9) - 1e-9;
+    return __double2float_rd(m - fabs(m) * 1e-9);
+}
+
 __global__ void __launch_bounds__(128) stage_kernel(const KParams P, const double* __restrict__ p,
                                                     double* __restrict__ staged)
 {
@@ -84,6 +96,7 @@ __global__ void __launch_bounds__(128) stage_kernel(const KParams P, const doubl
     for (int s = blockIdx.x; s < P.n_p; s += gridDim.x) {
         const double* pr = p + (size_t)s * L.np;
         double* S = staged + (size_t)s * L.total;
+        float* MG = reinterpret_cast<float*>(S + L.o_mg);
         const int tid = threadIdx.x, nt = blockDim.x;
         // header
         for (int i = tid; i < H_SIZE; i += nt) {
@@ -132,7 +145,7 @@ __global__ void __launch_bounds__(128) stage_kernel(const KParams P, const doubl
             const double ryi = t == 0 ? ry + P.vmargin + P.smargin : ry + P.vmargin;
             const double wgt = t == 0 ? 1000.0 : pr[L.p_qdyn + t - 1];
             double sa, ca;
-            sincos(q[4], &sa, &ca);
+            sincos_cw(q[4], &sa, &ca);
             double f[EF];
             f[E_CX] = q[0]; f[E_CY] = q[1]; f[E_CA] = ca; f[E_SA] = sa;
             f[E_I1I] = 1.0 / ((rxi + 1e-6) * (rxi + 1e-6));
@@ -146,6 +159,79 @@ __global__ void __launch_bounds__(128) stage_kernel(const KParams P, const doubl
                 else S[L.o_et + (m * L.Ndyn + ob) * N + (t - 1)] = f[m];
             }
         }
+        __syncthreads();   // the anchors (segment start points) and polygon rows are staged
+        // ---- culling tables, all relative to the anchors A_k = r_s[k]
+        const double* sg = S + L.o_seg;
+        for (int i = tid; i < L.Ndyn * N; i += nt) {          // i = ob*N + k
+            const int ob = i / N, k = i - ob * N;
+            const double ax = sg[k], ay = sg[N + k];
+            {   // t = 0 slot
+                const double* q = pr + L.p_od + (size_t)(ob * (N + 1)) * 6;
+                const double Rb = fmax(fabs(q[2] + P.vmargin + P.smargin + 1e-6), fabs(q[3] + P.vmargin + P.smargin + 1e-6));
+                MG[L.f_e0 + i] = margin_f(hypot_plain(q[0] - ax, q[1] - ay), Rb);
+            }
+            {   // t = k+1 slot
+                const double* q = pr + L.p_od + (size_t)(ob * (N + 1) + k + 1) * 6;
+                const double Rb = fmax(fabs(q[2] + P.vmargin + 1e-6), fabs(q[3] + P.vmargin + 1e-6));
+                MG[L.f_et + i] = margin_f(hypot_plain(q[0] - ax, q[1] - ay), Rb);
+            }
+        }
+        for (int i = tid; i < L.Nother * N; i += nt) {         // i = r*N + k
+            const int r = i / N, k = i - r * N;
+            const double ax = sg[k], ay = sg[N + k];
+            MG[L.f_c0 + i] = margin_f(hypot_plain(pr[L.p_c0 + 3 * r] - ax, pr[L.p_c0 + 3 * r + 1] - ay), P.dsafe);
+            MG[L.f_c + i] = margin_f(hypot_plain(pr[L.p_c + r * 3 * N + 3 * k] - ax,
+                                                 pr[L.p_c + r * 3 * N + 3 * k + 1] - ay), P.dsafe);
+        }
+        for (int i = tid; i < L.Nstc * N; i += nt) {           // i = pl*N + k
+            // a polygon is exactly zero wherever one half-plane value is <= 0: the bound is the
+            // largest distance by which the anchor violates an edge (zero rows: never active)
+            const int pl = i / N, k = i - pl * N;
+            const double ax = sg[k], ay = sg[N + k];
+            const double* q = pr + L.p_os + pl * 3 * L.nedge;
+            double m = -INFINITY;
+            for (int e = 0; e < L.nedge; ++e) {
+                const double a0 = q[L.nedge + e], a1 = q[2 * L.nedge + e];
+                const double r0 = q[e] - a0 * ax - a1 * ay;
+                const double an = sqrt(a0 * a0 + a1 * a1);
+                if (an > 0.0) m = fmax(m, -r0 / an);
+                else if (r0 <= 0.0) m = INFINITY;
+            }
+            MG[L.f_poly + i] = margin_f(m, 0.0);
+        }
+        // reference path: (k, i) -> min over segments i' >= i of dist(A_k, segment i')
+        for (int k = tid; k < N; k += nt) {
+            const double ax = sg[k], ay = sg[N + k];
+            double run = INFINITY;
+            for (int i = N - 1; i >= 0; --i) {
+                const double ex = ax - sg[i], ey = ay - sg[N + i];
+                const double ddx = sg[2 * N + i], ddy = sg[3 * N + i];
+                double t = (ex * ddx + ey * ddy) * sg[4 * N + i];
+                t = fmin(fmax(t, 0.0), 1.0);
+                const double vx = t * ddx - ex, vy = t * ddy - ey;
+                run = fmin(run, sqrt(vx * vx + vy * vy));
+                MG[L.f_seg + k * N + i] = margin_f(run, 0.0);
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < L.Ndyn + L.Nstc + 2 * L.Nother; i += nt) {   // per-item minimum over the steps
+            int it = i, base, base2 = -1;
+            if (it < L.Ndyn) { base = L.f_e0; base2 = L.f_et; }
+            else if ((it -= L.Ndyn) < L.Nstc) base = L.f_poly;
+            else if ((it -= L.Nstc) < L.Nother) base = L.f_c0;
+            else { it -= L.Nother; base = L.f_c; }
+            float m = __int_as_float(0x7f800000);
+            for (int k = 0; k < N; ++k) {
+                float t = MG[base + it * N + k];
+                m = (t < m || t != t) ? t : m;                 // NaN poisons the minimum: never skipped
+                if (base2 >= 0) {
+                    t = MG[base2 + it * N + k];
+                    m = (t < m || t != t) ? t : m;
+                }
+            }
+            MG[L.f_imin + i] = m;
+        }
+        __syncthreads();
     }
 }
 
@@ -284,6 +370,27 @@ __global__ void __launch_bounds__(256) solve_kernel(const KParams P, const doubl
     }
 }
 
+// K1 (queue variant): every warp pulls its own next instance from the atomic queue, so a
+// slow instance never holds other warps at a CTA barrier; scenario blocks are read from the
+// staged copy in global memory (L1/L2-resident: with culling a solve touches a few KB of it).
+template <int SPL>
+__global__ void __launch_bounds__(256, MPCB_MIN_CTAS) solve_kernel_queue(const KParams P, const double* __restrict__ staged,
+                                                          const SolveIO io, int* __restrict__ counter)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* lb_all = reinterpret_cast<double*>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* lb = lb_all + (size_t)warp * P.lb_doubles;
+    for (;;) {
+        int b = 0;
+        if (lane == 0) b = atomicAdd(counter, 1);
+        b = __shfl_sync(FULL, b, 0);
+        if (b >= P.B) break;
+        const double* S = staged + (size_t)(b / P.starts) * P.L.total;
+        solve_instance<SPL>(P, S, lb, b, lane, io);
+    }
+}
+
 // ------------------------------------------------------------------ host side
 int build_layout(const mpcb_dims* d, Lay& L)
 {
@@ -303,6 +410,16 @@ int build_layout(const mpcb_dims* d, Lay& L)
     L.o_poly = o; o += 3 * d->nedge * d->Nstc;
     L.o_e0 = o;   o += EF * d->Ndyn;
     L.o_et = o;   o += EF * d->Ndyn * N;
+    L.o_mg = o;
+    int fo = 0;
+    L.f_e0 = fo;   fo += d->Ndyn * N;
+    L.f_et = fo;   fo += d->Ndyn * N;
+    L.f_poly = fo; fo += d->Nstc * N;
+    L.f_c0 = fo;   fo += d->Nother * N;
+    L.f_c = fo;    fo += d->Nother * N;
+    L.f_imin = fo; fo += d->Ndyn + d->Nstc + 2 * d->Nother;
+    L.f_seg = fo;  fo += N * N;
+    o += (fo + 1) / 2;
     L.total = (o + 1) & ~1;
     int q = 0;
     L.p_um1 = q; q += 2;
@@ -319,6 +436,12 @@ int build_layout(const mpcb_dims* d, Lay& L)
     L.p_qdyn = q; q += N;
     L.np = q;
     return MPCB_OK;
+}
+
+int env_int(const char* name, int dflt)
+{
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
 }
 
 constexpr size_t WS_HEADER = 256;   // bytes reserved for the work-queue counter
@@ -343,6 +466,8 @@ int make_plan(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solver_cfg* c,
     if (rc) return rc;
     P.ts = r->ts; P.k6 = r->ts / 6.0; P.inv_ts = 1.0 / r->ts;
     P.ds2 = r->vehicle_width * r->vehicle_width;
+    P.dsafe = fabs(r->vehicle_width);
+    P.cull = env_int("MPCB_CULL", 1);
     P.vmargin = r->vehicle_margin; P.smargin = r->social_margin;
     P.vmin = r->lin_vel_min; P.vmax = r->lin_vel_max; P.wmax = r->ang_vel_max;
     P.amin = r->lin_acc_min; P.amax = r->lin_acc_max; P.wamax = r->ang_acc_max;
@@ -380,10 +505,13 @@ int make_plan(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solver_cfg* c,
             best_wps = wps; pl.smem = true; P.warps = W; P.nsc = nsc; pl.smem_bytes = need;
         }
     }
-    if (best_wps < 8) {   // too few resident warps: read the staged blocks through L1/L2 instead
+    const int mode = env_int("MPCB_MODE", 0);   // 0 auto (queue), 1 force shared-memory groups
+    if (best_wps < 8 || (mode != 1 && need_lbfgs)) {
+        // queue variant (solve) / too few resident warps: read the staged blocks through L1/L2
         pl.smem = false;
-        P.warps = 8; P.nsc = 0;
-        pl.smem_bytes = 16 + 8 * lbw;
+        P.warps = env_int("MPCB_WARPS", 8); P.nsc = 0;
+        if (P.warps < 1 || P.warps > 8) P.warps = 8;
+        pl.smem_bytes = 16 + P.warps * lbw;
     }
     return MPCB_OK;
 }
@@ -520,9 +648,23 @@ int32_t mpcb_solve_f64(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solve
         if (grid > ngroups) grid = ngroups;                                                        \
         solve_kernel<SPL, SM><<<grid, threads, pl.smem_bytes, st>>>(pl.P, staged, io, counter);    \
     } while (0)
-    if (pl.spl == 1) { if (pl.smem) LAUNCH_SOLVE(1, true); else LAUNCH_SOLVE(1, false); }
-    else             { if (pl.smem) LAUNCH_SOLVE(2, true); else LAUNCH_SOLVE(2, false); }
+#define LAUNCH_QUEUE(SPL)                                                                          \
+    do {                                                                                           \
+        rc = set_smem(solve_kernel_queue<SPL>, pl.smem_bytes);                                     \
+        if (rc) return rc;                                                                         \
+        int per_sm = 0;                                                                            \
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_kernel_queue<SPL>,   \
+                                                               threads, pl.smem_bytes));           \
+        if (per_sm < 1) per_sm = 1;                                                                \
+        if (env_int("MPCB_CTAS_PER_SM", 0) > 0) per_sm = env_int("MPCB_CTAS_PER_SM", 0);           \
+        int grid = sms * per_sm;                                                                   \
+        if (grid > ngroups) grid = ngroups;                                                        \
+        solve_kernel_queue<SPL><<<grid, threads, pl.smem_bytes, st>>>(pl.P, staged, io, counter);  \
+    } while (0)
+    if (pl.smem) { if (pl.spl == 1) LAUNCH_SOLVE(1, true); else LAUNCH_SOLVE(2, true); }
+    else         { if (pl.spl == 1) LAUNCH_QUEUE(1); else LAUNCH_QUEUE(2); }
 #undef LAUNCH_SOLVE
+#undef LAUNCH_QUEUE
     CUDA_TRY(cudaGetLastError());
     return MPCB_OK;
 }

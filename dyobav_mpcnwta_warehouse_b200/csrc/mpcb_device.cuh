@@ -4,16 +4,37 @@
 // registers, the rollout is a warp prefix scan, the adjoint a suffix scan, all
 // n=2N vector algebra of PANOC / L-BFGS is per-lane FMAs plus shuffle
 // reductions.  The scenario (one parameter row p, shared by all multi-start
-// guesses of that scenario) is a structure-of-arrays block in shared memory.
+// guesses of that scenario) is a structure-of-arrays block (shared memory via
+// TMA, or global memory through L1).
 //
 // What is computed follows the reference's problem definition
 // (mpc_builder.py:45-174, mpc_cost.py, mpc_helper.py, motion_model.py:141-163)
 // and OpEn's PANOC/ALM (see oracle/mpc_oracle.c for the restatement this is
 // checked against).
+//
+// ARITHMETIC CONTRACT (mirrored operation-for-operation by the "laned" oracle,
+// oracle/mpc_oracle_laned.c, which the GPU results must equal BIT FOR BIT):
+//   * compiled with -fmad=false: only the fma() calls written here fuse;
+//   * sums over the horizon are Kogge-Stone scans / xor-butterfly reductions in
+//     the order written in scan_incl / rscan_incl / warp_sum;
+//   * sin/cos come from sincos_cw below (Cody-Waite + fdlibm kernels), never
+//     from the CUDA math library;
+//   * obstacle terms that are provably zero (bounding-circle test around the
+//     step's reference point) are skipped — adding an exact 0.0 does not change a
+//     sum — and reference-path segments that provably cannot be the minimum are
+//     not evaluated: with MPCB_CULL=0 every term is evaluated and the results
+//     are bit-identical (tests/test_gpu_parity.py::test_culling_is_bit_exact).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
+
+#ifndef MPCB_RED_ATTR
+#define MPCB_RED_ATTR __noinline__
+#endif
+#ifndef MPCB_HELPER_ATTR
+#define MPCB_HELPER_ATTR __forceinline__
+#endif
 
 namespace mpcb {
 
@@ -27,6 +48,14 @@ enum { H_S0X = 0, H_S0Y, H_S0T, H_UM1V, H_UM1W, H_SNX, H_SNY, H_SNT, H_Q = 8, H_
 struct Lay {            // offsets (in doubles) inside one staged scenario block
     int N, Nother, Nstc, nedge, Ndyn;
     int o_hdr, o_rv, o_qstc, o_seg, o_c0, o_c, o_poly, o_e0, o_et;
+    int o_mg;           // float margins start here (offset in doubles)
+    // float sub-offsets (in floats) from o_mg.  Every table is [item][N]: entry (item, k) is a
+    // conservative lower bound of the distance the robot must be from the anchor A_k = r_s[k]
+    // (the reference point of step k) before that item can contribute at step k.
+    int f_e0, f_et, f_poly, f_c0, f_c;
+    int f_imin;         // per-item minimum over the steps: [Ndyn] ellipses (both slots), then
+                        // [Nstc] polygons, [Nother] robots at t=0, [Nother] predicted robots
+    int f_seg;          // [N][N]: (k, i) -> min over segments i' >= i of dist(A_k, segment i')
     int total;          // doubles, multiple of 2 (16-byte granularity for TMA bulk copies)
     int np;             // length of a raw parameter row
     // raw p offsets (mpc_builder.py:47-60)
@@ -35,23 +64,53 @@ struct Lay {            // offsets (in doubles) inside one staged scenario block
 
 struct KParams {
     Lay L;
-    double ts, k6, inv_ts, ds2, vmargin, smargin;
+    double ts, k6, inv_ts, ds2, dsafe, vmargin, smargin;
     double vmin, vmax, wmax, amin, amax, wamax;
     double tol, tol0, delta, beta, rho, theta, c_init, sy_eps, cb_eps, cb_alpha;
     int max_inner, max_outer, mem;
     int n_p, starts, B;
-    int warps, nsc;      // warps per CTA, scenario blocks per CTA
+    int warps, nsc;      // warps per CTA, scenario blocks per CTA (shared-memory variant)
     int lb_doubles;      // per-warp L-BFGS scratch (doubles)
+    int cull;            // 1: skip provably-zero obstacle terms
 };
 
+// ---------------------------------------------------------------- sin / cos
+// Cody-Waite reduction by pi/2 (two constants, exact first product for
+// |n| < 2^20) + the fdlibm __kernel_sin/__kernel_cos polynomials in Horner
+// form.  |error| ~ 1 ulp for |x| < 1e5; identical code in the laned oracle.
+__device__ MPCB_HELPER_ATTR void sincos_cw(double x, double* sn, double* cs)
+{
+    const double fn = rint(x * 6.36619772367581382433e-01);
+    double r = fma(-fn, 1.57079632673412561417e+00, x);
+    r = fma(-fn, 6.07710050650619224932e-11, r);
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double s = fma(r * z, ps, r);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double c = fma(z * z, pc, fma(-0.5, z, 1.0));
+    const int q = static_cast<int>(fn) & 3;
+    const double s1 = (q & 1) ? c : s;
+    const double c1 = (q & 1) ? s : c;
+    *sn = (q & 2) ? -s1 : s1;
+    *cs = ((q + 1) & 2) ? -c1 : c1;
+}
+
 // ---------------------------------------------------------------- warp helpers
-__device__ __forceinline__ double warp_sum(double v)
+__device__ MPCB_RED_ATTR double warp_sum(double v)
 {
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(FULL, v, m);
     return v;
 }
-__device__ __forceinline__ double scan_incl(double v, int lane)
+__device__ MPCB_RED_ATTR double scan_incl(double v, int lane)
 {
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -60,7 +119,7 @@ __device__ __forceinline__ double scan_incl(double v, int lane)
     }
     return v;
 }
-__device__ __forceinline__ double rscan_incl(double v, int lane)
+__device__ MPCB_RED_ATTR double rscan_incl(double v, int lane)
 {
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -86,6 +145,17 @@ __device__ __forceinline__ void prefix(const double (&a)[SPL], double (&excl)[SP
         if (SPL > 1) carry += __shfl_sync(FULL, s, 31);
     }
 }
+template <int SPL>
+__device__ __forceinline__ void prefix_incl(const double (&a)[SPL], double (&incl)[SPL], int lane)
+{
+    double carry = 0.0;
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+        double s = scan_incl(a[j], lane);
+        incl[j] = carry + s;
+        if (SPL > 1) carry += __shfl_sync(FULL, s, 31);
+    }
+}
 // suffix sums: incl[j] = sum over steps >= own, excl[j] = sum over steps > own
 template <int SPL>
 __device__ __forceinline__ void suffix(const double (&a)[SPL], double (&excl)[SPL],
@@ -98,6 +168,17 @@ __device__ __forceinline__ void suffix(const double (&a)[SPL], double (&excl)[SP
         double e = __shfl_down_sync(FULL, s, 1);
         if (lane == 31) e = 0.0;
         excl[j] = carry + e;
+        incl[j] = carry + s;
+        if (SPL > 1) carry += __shfl_sync(FULL, s, 0);
+    }
+}
+template <int SPL>
+__device__ __forceinline__ void suffix_incl(const double (&a)[SPL], double (&incl)[SPL], int lane)
+{
+    double carry = 0.0;
+#pragma unroll
+    for (int j = SPL - 1; j >= 0; --j) {
+        double s = rscan_incl(a[j], lane);
         incl[j] = carry + s;
         if (SPL > 1) carry += __shfl_sync(FULL, s, 0);
     }
@@ -120,7 +201,7 @@ struct EllT {  // everything one ellipse slot contributes
 
 // mpc_helper.py:38-52 / mpc_cost.py:26-44.  `f` points at field 0 of the slot,
 // consecutive fields are `stride` doubles apart.
-__device__ __forceinline__ void ellipse_terms(const bool GRAD, const double* __restrict__ f, int stride,
+__device__ MPCB_HELPER_ATTR void ellipse_terms(const bool GRAD, const double* __restrict__ f, int stride,
                                               double x, double y, EllT& o)
 {
     const double ex = x - f[E_CX * stride], ey = y - f[E_CY * stride];
@@ -156,18 +237,21 @@ __device__ __forceinline__ void ellipse_terms(const bool GRAD, const double* __r
 }
 
 // mpc_helper.py:54-75: I = prod_e max(0, b_e - a0_e x - a1_e y); rows {b,-a0,-a1}
-__device__ __forceinline__ double polygon_ind(const bool GRAD, const double* __restrict__ e, int nedge,
+__device__ MPCB_HELPER_ATTR double polygon_ind(const bool GRAD, const double* __restrict__ e, int nedge,
                                               double x, double y, double& dIx, double& dIy)
 {
     double I = 1.0;
+#pragma unroll 1
     for (int j = 0; j < nedge; ++j) {
         const double r = fma(e[3 * j + 2], y, fma(e[3 * j + 1], x, e[3 * j]));
         I *= fmax(0.0, r);
     }
     dIx = 0.0; dIy = 0.0;
     if (GRAD && I > 0.0) {
+#pragma unroll 1
         for (int j = 0; j < nedge; ++j) {
             double pr = 1.0;
+#pragma unroll 1
             for (int m = 0; m < nedge; ++m)
                 if (m != j) pr *= fma(e[3 * m + 2], y, fma(e[3 * m + 1], x, e[3 * m]));
             dIx = fma(pr, e[3 * j + 1], dIx);
@@ -189,8 +273,11 @@ struct EvalOut {
 // Evaluate psi(u; c, y) (and its gradient) for the instance owned by this warp.
 //   S: staged scenario block.  v/w: the point.  ya/yw: multipliers of the lane's
 //   two F1 entries (acc_k, wacc_k).  F2out (nullable, global): per-obstacle F2.
+#ifndef MPCB_EVAL_ATTR
+#define MPCB_EVAL_ATTR __forceinline__
+#endif
 template <int SPL>
-__device__ __forceinline__ void eval_psi(const KParams& P, const double* __restrict__ S,
+__device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restrict__ S,
                                          const double (&v)[SPL], const double (&w)[SPL], double c,
                                          const double (&ya)[SPL], const double (&yw)[SPL],
                                          const bool GRAD, EvalOut<SPL>& out, int lane,
@@ -200,8 +287,8 @@ __device__ __forceinline__ void eval_psi(const KParams& P, const double* __restr
     const int N = L.N;
     const double* H = S + L.o_hdr;
     const double* q = H + H_Q;
-    const double qvel = q[1], rv = q[3], rw = q[4], qN = q[5], qthN = q[6], qrpd = q[7];
-    const double accp = q[8], waccp = q[9];
+    const float* MG = reinterpret_cast<const float*>(S + L.o_mg);
+    const bool CULL = P.cull != 0;
 
     bool act[SPL];
     int kk[SPL];
@@ -216,50 +303,107 @@ __device__ __forceinline__ void eval_psi(const KParams& P, const double* __restr
 #pragma unroll
     for (int j = 0; j < SPL; ++j) dth[j] = act[j] ? P.ts * w[j] : 0.0;
     prefix<SPL>(dth, th, thn, lane);
-    double Cc[SPL], Ss[SPL], cb[SPL], sb[SPL], cc[SPL], sc[SPL], dx[SPL], dy[SPL];
+    double c0s[SPL], s0s[SPL], cb[SPL], sb[SPL];
 #pragma unroll
     for (int j = 0; j < SPL; ++j) {
         const double t0 = H[H_S0T] + th[j];
         const double tb = t0 + 0.5 * dth[j];
-        const double tc = H[H_S0T] + thn[j];
-        double s0, c0;
-        sincos(t0, &s0, &c0);
-        sincos(tb, &sb[j], &cb[j]);
-        sincos(tc, &sc[j], &cc[j]);
-        Cc[j] = c0 + 4.0 * cb[j] + cc[j];
-        Ss[j] = s0 + 4.0 * sb[j] + sc[j];
+        sincos_cw(t0, &s0s[j], &c0s[j]);
+        sincos_cw(tb, &sb[j], &cb[j]);
+    }
+    // cos/sin of the end-of-step heading = the next step's start heading: take
+    // it from the next lane (the lane after the last step holds theta_N)
+    double cc[SPL], sc[SPL], Cc[SPL], Ss[SPL], dx[SPL], dy[SPL];
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+        double cn = __shfl_down_sync(FULL, c0s[j], 1), sn = __shfl_down_sync(FULL, s0s[j], 1);
+        if (j + 1 < SPL) {
+            const double c2 = __shfl_sync(FULL, c0s[j + 1 < SPL ? j + 1 : j], 0);
+            const double s2 = __shfl_sync(FULL, s0s[j + 1 < SPL ? j + 1 : j], 0);
+            if (lane == 31) { cn = c2; sn = s2; }
+        } else if (N == 32 * SPL) {   // no lane after the last step: compute it
+            if (lane == 31) sincos_cw(H[H_S0T] + thn[j], &sn, &cn);
+        }
+        cc[j] = cn; sc[j] = sn;
+        Cc[j] = c0s[j] + 4.0 * cb[j] + cc[j];
+        Ss[j] = s0s[j] + 4.0 * sb[j] + sc[j];
         const double kv = act[j] ? P.k6 * v[j] : 0.0;
         dx[j] = kv * Cc[j];
         dy[j] = kv * Ss[j];
     }
-    double px[SPL], py[SPL], tmp[SPL];
-    prefix<SPL>(dx, tmp, px, lane);
-    prefix<SPL>(dy, tmp, py, lane);
+    double px[SPL], py[SPL];
+    prefix_incl<SPL>(dx, px, lane);
+    prefix_incl<SPL>(dy, py, lane);
 
+    const double qvel = q[1], rv = q[3], rw = q[4], qrpd = q[7];
     double cost = 0.0;
     double gx[SPL], gy[SPL], gvd[SPL], gwd[SPL];
     double Spoly[SPL], dSx[SPL], dSy[SPL];
+    double X[SPL], Y[SPL];
+    float Df[SPL];
     bool anyhinge = false;
+    const double* sg = S + L.o_seg;
+
+    // positions and, per step, the distance to the step's anchor (its reference point),
+    // inflated and rounded up: every culling test compares a precomputed lower bound with it
+    float dmax = 0.f;
+    {
+        bool bad = false;
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) {
+            const int k = act[j] ? kk[j] : N - 1;
+            X[j] = H[H_S0X] + px[j];
+            Y[j] = H[H_S0Y] + py[j];
+            const double ax = X[j] - sg[k], ay = Y[j] - sg[N + k];
+            Df[j] = CULL ? __double2float_ru(fma(sqrt(fma(ax, ax, ay * ay)), 1.0 + 1e-9, 1e-9))
+                         : __int_as_float(0x7f800000);
+            if (act[j]) {
+                dmax = fmaxf(dmax, Df[j]);
+                bad |= !(Df[j] < __int_as_float(0x7f800000));
+            }
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(FULL, dmax, m));
+        if (__any_sync(FULL, bad)) dmax = __int_as_float(0x7f800000);   // non-finite state: cull nothing
+    }
+    const float* IM_E = MG + L.f_imin;
+    const float* IM_P = IM_E + L.Ndyn;
+    const float* IM_C0 = IM_P + L.Nstc;
+    const float* IM_C = IM_C0 + L.Nother;
 
 #pragma unroll
     for (int j = 0; j < SPL; ++j) {
         const int k = act[j] ? kk[j] : N - 1;   // clamped index for loads
-        const double x = H[H_S0X] + px[j], y = H[H_S0Y] + py[j];
+        const double x = X[j], y = Y[j];
+        const float D = Df[j];
         double cst = 0.0, ggx = 0.0, ggy = 0.0;
 
-        // -- reference path: qrpd * min_{i>=k} dist^2(p, seg_i)   (mpc_cost.py:84-95)
+        // -- reference path: qrpd * min_{i>=k} dist^2(p, seg_i)   (mpc_cost.py:84-95).
+        //    Segments are visited from i = k; the walk stops once the precomputed bound
+        //    says no later segment can beat the current minimum.
         {
-            const double* sg = S + L.o_seg;
+            const float* tm = MG + L.f_seg + k * N;
             double best = INFINITY;
             int ib = k;
-            for (int i = 0; i < N; ++i) {       // uniform loop: broadcast loads
-                const double ex = x - sg[i], ey = y - sg[N + i];
-                const double ddx = sg[2 * N + i], ddy = sg[3 * N + i];
-                const double th_ = fma(ex, ddx, ey * ddy) * sg[4 * N + i];
-                const double ts_ = fmin(fmax(th_, 0.0), 1.0);
-                const double vx = fma(ts_, ddx, -ex), vy = fma(ts_, ddy, -ey);
-                const double d2 = fma(vx, vx, vy * vy);
-                if (i >= k && d2 < best) { best = d2; ib = i; }
+            bool alive = true;
+#pragma unroll 1
+            for (int i = k; __any_sync(FULL, alive); ++i) {
+                if (alive) {
+                    if (i >= N) { alive = false; }
+                    else {
+                        const float lb = tm[i] - D;
+                        if (lb > 0.f && (double)lb * (double)lb * (1.0 - 1e-6) > best) { alive = false; }
+                        else {
+                            const double ex = x - sg[i], ey = y - sg[N + i];
+                            const double ddx = sg[2 * N + i], ddy = sg[3 * N + i];
+                            const double th_ = fma(ex, ddx, ey * ddy) * sg[4 * N + i];
+                            const double ts_ = fmin(fmax(th_, 0.0), 1.0);
+                            const double vx = fma(ts_, ddx, -ex), vy = fma(ts_, ddy, -ey);
+                            const double d2 = fma(vx, vx, vy * vy);
+                            if (d2 < best) { best = d2; ib = i; }
+                        }
+                    }
+                }
             }
             cst = best * qrpd;
             if (GRAD) {
@@ -282,27 +426,43 @@ __device__ __forceinline__ void eval_psi(const KParams& P, const double* __restr
             gvd[j] = 2.0 * qvel * dv + 2.0 * rv * v[j];
             gwd[j] = 2.0 * rw * w[j];
         }
-        // -- fleet: linear hinge on squared distance (mpc_cost.py:65-76)
+        // -- fleet: linear hinge on squared distance (mpc_cost.py:65-76).  A ballot over the
+        //    per-item bounds yields the robots that can matter for ANY step of this evaluation;
+        //    their bits are walked in index order, so sums keep the order of the full loop.
         {
+            double s1 = 0.0, s2 = 0.0;
             const double* c0x = S + L.o_c0;
             const double* c0y = c0x + L.Nother;
-            double s1 = 0.0, s2 = 0.0;
-            for (int r = 1; r < L.Nother; ++r) {     // robot 0 skipped (mpc_builder.py:86-87)
-                const double ex = x - c0x[r], ey = y - c0y[r];
-                const double h = P.ds2 - fma(ex, ex, ey * ey);
-                if (h > 0.0) {
-                    s1 += h;
-                    if (GRAD) { ggx = fma(-2000.0, ex, ggx); ggy = fma(-2000.0, ey, ggy); }
-                }
-            }
+            const float* m0 = MG + L.f_c0 + k;
             const double* cx_ = S + L.o_c;
             const double* cy_ = cx_ + L.Nother * N;
-            for (int r = 0; r < L.Nother; ++r) {
-                const double ex = x - cx_[r * N + k], ey = y - cy_[r * N + k];
-                const double h = P.ds2 - fma(ex, ex, ey * ey);
-                if (h > 0.0) {
-                    s2 += h;
-                    if (GRAD) { ggx = fma(-20.0, ex, ggx); ggy = fma(-20.0, ey, ggy); }
+            const float* m1 = MG + L.f_c + k;
+#pragma unroll 1
+            for (int base = 0; base < L.Nother; base += 32) {
+                const int it = base + lane;
+                unsigned ma = __ballot_sync(FULL, it >= 1 && it < L.Nother && !(IM_C0[it < L.Nother ? it : 0] > dmax));
+                unsigned mb = __ballot_sync(FULL, it < L.Nother && !(IM_C[it < L.Nother ? it : 0] > dmax));
+                while (ma) {                              // robot 0 skipped (mpc_builder.py:86-87)
+                    const int r = base + __ffs(ma) - 1;
+                    ma &= ma - 1;
+                    if (m0[r * N] > D) continue;
+                    const double ex = x - c0x[r], ey = y - c0y[r];
+                    const double h = P.ds2 - fma(ex, ex, ey * ey);
+                    if (h > 0.0) {
+                        s1 += h;
+                        if (GRAD) { ggx = fma(-2000.0, ex, ggx); ggy = fma(-2000.0, ey, ggy); }
+                    }
+                }
+                while (mb) {
+                    const int r = base + __ffs(mb) - 1;
+                    mb &= mb - 1;
+                    if (m1[r * N] > D) continue;
+                    const double ex = x - cx_[r * N + k], ey = y - cy_[r * N + k];
+                    const double h = P.ds2 - fma(ex, ex, ey * ey);
+                    if (h > 0.0) {
+                        s2 += h;
+                        if (GRAD) { ggx = fma(-20.0, ex, ggx); ggy = fma(-20.0, ey, ggy); }
+                    }
                 }
             }
             cst = fma(1000.0, s1, cst);
@@ -313,18 +473,27 @@ __device__ __forceinline__ void eval_psi(const KParams& P, const double* __restr
         {
             const double qs = S[L.o_qstc + k];
             const double* pe = S + L.o_poly;
-            for (int i = 0; i < L.Nstc; ++i) {
-                double dIx, dIy;
-                const double I = polygon_ind(GRAD, pe + i * 3 * L.nedge, L.nedge, x, y, dIx, dIy);
-                if (I > 0.0) {
-                    cst = fma(qs, I * I, cst);
-                    sp += I;
-                    if (GRAD) {
-                        const double m = 2.0 * qs * I;
-                        ggx = fma(m, dIx, ggx);
-                        ggy = fma(m, dIy, ggy);
-                        spx += dIx;
-                        spy += dIy;
+            const float* mp = MG + L.f_poly + k;
+#pragma unroll 1
+            for (int base = 0; base < L.Nstc; base += 32) {
+                const int it = base + lane;
+                unsigned mk = __ballot_sync(FULL, it < L.Nstc && !(IM_P[it < L.Nstc ? it : 0] > dmax));
+                while (mk) {
+                    const int i = base + __ffs(mk) - 1;
+                    mk &= mk - 1;
+                    if (mp[i * N] > D) continue;
+                    double dIx, dIy;
+                    const double I = polygon_ind(GRAD, pe + i * 3 * L.nedge, L.nedge, x, y, dIx, dIy);
+                    if (I > 0.0) {
+                        cst = fma(qs, I * I, cst);
+                        sp += I;
+                        if (GRAD) {
+                            const double m = 2.0 * qs * I;
+                            ggx = fma(m, dIx, ggx);
+                            ggy = fma(m, dIy, ggy);
+                            spx += dIx;
+                            spy += dIy;
+                        }
                     }
                 }
             }
@@ -334,13 +503,30 @@ __device__ __forceinline__ void eval_psi(const KParams& P, const double* __restr
         {
             const double* e0 = S + L.o_e0;
             const double* et = S + L.o_et + k;
-            for (int i = 0; i < L.Ndyn; ++i) {
-                EllT a, b;
-                ellipse_terms(GRAD, e0 + i, L.Ndyn, x, y, a);
-                ellipse_terms(GRAD, et + i * N, L.Ndyn * N, x, y, b);
-                cst += a.cost + b.cost;
-                if (GRAD) { ggx += a.gx + b.gx; ggy += a.gy + b.gy; }
-                hinge |= (a.hr > 0.0) | (b.hr > 0.0);
+            const float* me0 = MG + L.f_e0 + k;
+            const float* met = MG + L.f_et + k;
+#pragma unroll 1
+            for (int base = 0; base < L.Ndyn; base += 32) {
+                const int it = base + lane;
+                unsigned mk = __ballot_sync(FULL, it < L.Ndyn && !(IM_E[it < L.Ndyn ? it : 0] > dmax));
+                while (mk) {
+                    const int i = base + __ffs(mk) - 1;
+                    mk &= mk - 1;
+                    if (!(me0[i * N] > D)) {
+                        EllT a;
+                        ellipse_terms(GRAD, e0 + i, L.Ndyn, x, y, a);
+                        cst += a.cost;
+                        if (GRAD) { ggx += a.gx; ggy += a.gy; }
+                        hinge |= a.hr > 0.0;
+                    }
+                    if (!(met[i * N] > D)) {
+                        EllT b;
+                        ellipse_terms(GRAD, et + i * N, L.Ndyn * N, x, y, b);
+                        cst += b.cost;
+                        if (GRAD) { ggx += b.gx; ggy += b.gy; }
+                        hinge |= b.hr > 0.0;
+                    }
+                }
             }
         }
         if (!act[j]) { cst = 0.0; ggx = 0.0; ggy = 0.0; sp = 0.0; spx = 0.0; spy = 0.0; hinge = false; gvd[j] = 0.0; gwd[j] = 0.0; }
@@ -353,6 +539,7 @@ __device__ __forceinline__ void eval_psi(const KParams& P, const double* __restr
     // ---- terminal cost on the last state (mpc_builder.py:148)
     double gthN = 0.0;
     {
+        const double qN = q[5], qthN = q[6];
 #pragma unroll
         for (int j = 0; j < SPL; ++j) {
             if (act[j] && kk[j] == N - 1) {
@@ -369,7 +556,6 @@ __device__ __forceinline__ void eval_psi(const KParams& P, const double* __restr
     // ---- penalty constraints F2 (mpc_builder.py:72,106,119,137; vector of Ndyn
     //      with the polygon hinge broadcast into every entry)
     double f2sq = 0.0;
-    const int n2 = L.Ndyn > 0 ? L.Ndyn : 1;
     if (__any_sync(FULL, anyhinge) || F2out != nullptr) {
         double spl = 0.0;
 #pragma unroll
@@ -381,29 +567,41 @@ __device__ __forceinline__ void eval_psi(const KParams& P, const double* __restr
             sumF2 = SP;
             if (F2out && lane == 0) F2out[0] = SP;
         }
-        for (int i = 0; i < L.Ndyn; ++i) {
-            double hl = 0.0;
-            EllT a[SPL], b[SPL];
+#pragma unroll 1
+        for (int base = 0; base < L.Ndyn; base += 32) {
+            const int it = base + lane;
+            const unsigned mk = __ballot_sync(FULL, it < L.Ndyn && !(IM_E[it < L.Ndyn ? it : 0] > dmax));
+            const int lim = L.Ndyn - base < 32 ? L.Ndyn - base : 32;
+#pragma unroll 1
+            for (int bi = 0; bi < lim; ++bi) {
+                const int i = base + bi;
+                double F2i = SP;
+                EllT a[SPL], b[SPL];
+                const bool cand = (mk >> bi) & 1u;
+                if (cand) {     // an obstacle outside the mask cannot have a positive hinge
+                    double hl = 0.0;
 #pragma unroll
-            for (int j = 0; j < SPL; ++j) {
-                const int k = act[j] ? kk[j] : N - 1;
-                const double x = H[H_S0X] + px[j], y = H[H_S0Y] + py[j];
-                ellipse_terms(GRAD, S + L.o_e0 + i, L.Ndyn, x, y, a[j]);
-                ellipse_terms(GRAD, S + L.o_et + k + i * N, L.Ndyn * N, x, y, b[j]);
-                if (!act[j]) { a[j].hr = 0.0; b[j].hr = 0.0; }
-                hl += a[j].hr + b[j].hr;
-            }
-            double F2i = SP;
-            if (__any_sync(FULL, hl > 0.0)) F2i += warp_sum(hl);
-            if (F2out && lane == 0) F2out[i] = F2i;
-            f2sq = fma(F2i, F2i, f2sq);
-            sumF2 += F2i;
-            if (GRAD && F2i > 0.0) {
-                const double m = c * F2i;
+                    for (int j = 0; j < SPL; ++j) {
+                        const int k = act[j] ? kk[j] : N - 1;
+                        a[j].hr = 0.0; b[j].hr = 0.0;
+                        if (act[j] && !(MG[L.f_e0 + i * N + k] > Df[j]))
+                            ellipse_terms(GRAD, S + L.o_e0 + i, L.Ndyn, X[j], Y[j], a[j]);
+                        if (act[j] && !(MG[L.f_et + i * N + k] > Df[j]))
+                            ellipse_terms(GRAD, S + L.o_et + k + i * N, L.Ndyn * N, X[j], Y[j], b[j]);
+                        hl += a[j].hr + b[j].hr;
+                    }
+                    if (__any_sync(FULL, hl > 0.0)) F2i += warp_sum(hl);
+                }
+                if (F2out && lane == 0) F2out[i] = F2i;
+                f2sq = fma(F2i, F2i, f2sq);
+                sumF2 += F2i;
+                if (cand && GRAD && F2i > 0.0) {
+                    const double m = c * F2i;
 #pragma unroll
-                for (int j = 0; j < SPL; ++j) {
-                    if (a[j].hr > 0.0) { gx[j] = fma(m, a[j].hrx, gx[j]); gy[j] = fma(m, a[j].hry, gy[j]); }
-                    if (b[j].hr > 0.0) { gx[j] = fma(m, b[j].hrx, gx[j]); gy[j] = fma(m, b[j].hry, gy[j]); }
+                    for (int j = 0; j < SPL; ++j) {
+                        if (a[j].hr > 0.0) { gx[j] = fma(m, a[j].hrx, gx[j]); gy[j] = fma(m, a[j].hry, gy[j]); }
+                        if (b[j].hr > 0.0) { gx[j] = fma(m, b[j].hrx, gx[j]); gy[j] = fma(m, b[j].hry, gy[j]); }
+                    }
                 }
             }
         }
@@ -416,12 +614,12 @@ __device__ __forceinline__ void eval_psi(const KParams& P, const double* __restr
             }
         }
     }
-    (void)n2;
 
     // ---- accelerations: cost, ALM term on F1 (mpc_builder.py:156-169)
     double gFa[SPL], gFw[SPL];
     double dist2 = 0.0;
     {
+        const double accp = q[8], waccp = q[9];
         const double cdiv = fmax(c, 1.0);
         double vprev_carry = H[H_UM1V], wprev_carry = H[H_UM1W];
 #pragma unroll
@@ -459,8 +657,8 @@ __device__ __forceinline__ void eval_psi(const KParams& P, const double* __restr
         // adjoint: G = sum_{j>=k} g_j ; theta coupling via a second suffix sum
         double Gx[SPL], Gy[SPL], hh[SPL], Hex[SPL], Hin[SPL];
         const double gthN_all = warp_sum(gthN);   // only the lane owning step N-1 is non-zero
-        suffix<SPL>(gx, tmp, Gx, lane);
-        suffix<SPL>(gy, tmp, Gy, lane);
+        suffix_incl<SPL>(gx, Gx, lane);
+        suffix_incl<SPL>(gy, Gy, lane);
 #pragma unroll
         for (int j = 0; j < SPL; ++j) hh[j] = fma(Gy[j], dx[j], -(Gx[j] * dy[j]));
         suffix<SPL>(hh, Hex, Hin, lane);

@@ -145,6 +145,7 @@ __device__ __forceinline__ void lbfgs_apply(Lbfgs<SPL>& B, double (&q0)[SPL], do
                                             int lane, const bool (&act)[SPL])
 {
     if (B.active == 0) return;
+#pragma unroll 1
     for (int k = 0; k < B.active; ++k) {
         const int row = B.phys(k);
         const double* sr = B.s + row * 2 * B.N;
@@ -162,6 +163,7 @@ __device__ __forceinline__ void lbfgs_apply(Lbfgs<SPL>& B, double (&q0)[SPL], do
     }
     __syncwarp();
     MPCB_FORJ { q0[j] *= B.gamma; q1[j] *= B.gamma; }
+#pragma unroll 1
     for (int k = B.active - 1; k >= 0; --k) {
         const int row = B.phys(k);
         const double* sr = B.s + row * 2 * B.N;

@@ -18,8 +18,8 @@ _dp = ctypes.POINTER(ctypes.c_double)
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "libmpc_oracle.so")
-    src = os.path.join(_HERE, "mpc_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("mpc_oracle.c", "mpc_oracle_laned.c", "Makefile")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return so
 
@@ -32,6 +32,9 @@ def lib():
         L.mpco_eval.restype = ctypes.c_int32
         L.mpco_solve.restype = ctypes.c_int32
         L.mpco_solve_batch.restype = ctypes.c_int32
+        L.mpcl_eval.restype = ctypes.c_int32
+        L.mpcl_solve.restype = ctypes.c_int32
+        L.mpcl_solve_batch.restype = ctypes.c_int32
         for f in (L.mpco_dist_to_lineseg, L.mpco_inside_ellipse, L.mpco_inside_cvx_polygon):
             f.restype = ctypes.c_double
         L.mpco_dist_to_lineseg.argtypes = [ctypes.c_double] * 6
@@ -52,9 +55,10 @@ def _c(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
 
 
-def evaluate(dims, robot, p, u, y=None, c=10.0, want_grad=True):
-    """f, psi, grad psi, F1, F2 for one instance."""
+def evaluate(dims, robot, p, u, y=None, c=10.0, want_grad=True, laned=False):
+    """f, psi, grad psi, F1, F2 for one instance (laned=True: the kernel's operation order)."""
     L = lib()
+    fn = L.mpcl_eval if laned else L.mpco_eval
     cd, cr = dims.to_c(), robot.to_c()
     p, u, y = _c(p), _c(u), _c(y)
     assert p.shape == (dims.np,) and u.shape == (dims.nu_total,)
@@ -63,7 +67,7 @@ def evaluate(dims, robot, p, u, y=None, c=10.0, want_grad=True):
     g = np.zeros(dims.nu_total) if want_grad else None
     F1 = np.zeros(dims.n1)
     F2 = np.zeros(dims.n2)
-    rc = L.mpco_eval(ctypes.byref(cd), ctypes.byref(cr), _p(p), _p(u), _p(y),
+    rc = fn(ctypes.byref(cd), ctypes.byref(cr), _p(p), _p(u), _p(y),
                      ctypes.c_double(c), ctypes.byref(f), ctypes.byref(psi), _p(g), _p(F1), _p(F2))
     if rc:
         raise RuntimeError(f"mpco_eval failed: {rc}")
@@ -74,15 +78,16 @@ SCALARS = ("cost", "fpr", "f1_infeas", "f2_norm", "penalty", "n_outer", "n_inner
            "n_cost", "n_grad", "exit_status")
 
 
-def solve(dims, robot, cfg, p, u0=None, y0=None, c0=None):
+def solve(dims, robot, cfg, p, u0=None, y0=None, c0=None, laned=False):
     L = lib()
+    fn = L.mpcl_solve if laned else L.mpco_solve
     cd, cr, cc = dims.to_c(), robot.to_c(), cfg.to_c()
     p, u0, y0 = _c(p), _c(u0), _c(y0)
     u = np.zeros(dims.nu_total)
     y = np.zeros(dims.n1)
     sc = np.zeros(10)
     c0p = None if c0 is None else ctypes.byref(ctypes.c_double(c0))
-    rc = L.mpco_solve(ctypes.byref(cd), ctypes.byref(cr), ctypes.byref(cc), _p(p), _p(u0),
+    rc = fn(ctypes.byref(cd), ctypes.byref(cr), ctypes.byref(cc), _p(p), _p(u0),
                       _p(y0), c0p, _p(u), _p(y), _p(sc))
     if rc:
         raise RuntimeError(f"mpco_solve failed: {rc}")
@@ -94,7 +99,7 @@ def solve(dims, robot, cfg, p, u0=None, y0=None, c0=None):
     return out
 
 
-def solve_batch(dims, robot, cfg, P, U0=None, starts=1, threads=1):
+def solve_batch(dims, robot, cfg, P, U0=None, starts=1, threads=1, laned=False):
     """OpenMP batch driver; P [n_p, np], U0 [n_p*starts, 2N] or None."""
     L = lib()
     cd, cr, cc = dims.to_c(), robot.to_c(), cfg.to_c()
@@ -103,9 +108,14 @@ def solve_batch(dims, robot, cfg, P, U0=None, starts=1, threads=1):
     B = n_p * starts
     U = np.zeros((B, dims.nu_total))
     SC = np.zeros((B, 10))
-    rc = L.mpco_solve_batch(ctypes.byref(cd), ctypes.byref(cr), ctypes.byref(cc),
-                            ctypes.c_int32(n_p), ctypes.c_int32(starts), _p(P), _p(U0),
-                            _p(U), _p(SC), ctypes.c_int32(threads))
+    if laned:
+        rc = L.mpcl_solve_batch(ctypes.byref(cd), ctypes.byref(cr), ctypes.byref(cc),
+                                ctypes.c_int32(n_p), ctypes.c_int32(starts), _p(P), _p(U0),
+                                _p(U), _p(SC), ctypes.c_int32(dims.np), ctypes.c_int32(threads))
+    else:
+        rc = L.mpco_solve_batch(ctypes.byref(cd), ctypes.byref(cr), ctypes.byref(cc),
+                                ctypes.c_int32(n_p), ctypes.c_int32(starts), _p(P), _p(U0),
+                                _p(U), _p(SC), ctypes.c_int32(threads))
     if rc:
         raise RuntimeError(f"mpco_solve_batch failed: {rc}")
     return U, SC
