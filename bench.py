@@ -103,7 +103,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scenarios", type=int, default=8192, help="scenarios per GPU (x8 starts)")
     ap.add_argument("--starts", type=int, default=8)
-    ap.add_argument("--cpu-solves", type=int, default=0, help="CPU sample size (0: 2 per core, >= 16)")
+    ap.add_argument("--cpu-solves", type=int, default=0, help="CPU sample size (0: 24 per core)")
+    ap.add_argument("--latency-solves", type=int, default=24, help="single-solve latency sample (0: skip)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
 
@@ -124,7 +125,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        n_solves = args.cpu_solves or max(16, 2 * cores)
+        n_solves = args.cpu_solves or max(16, 8 * cores)
         n_p = max(1, n_solves // starts)
         P = instances.generate(dims, n_p, seed=instances.BASE_SEED + 4)
         U0 = instances.multistart_guesses(dims, P, starts, instances.BASE_SEED + 4)
@@ -161,10 +162,13 @@ def main():
     from dyobav_mpcnwta_warehouse_b200.csrc import build as cbuild
     cbuild.build()
 
-    seed = instances.BASE_SEED + 4 + 1000 * rank          # each rank owns its scenarios
-    P = instances.generate(dims, args.scenarios, seed=seed)
+    from dyobav_mpcnwta_warehouse_b200 import sharding
+    n_global = args.scenarios * world                     # weak scaling: 8192 scenarios per GPU
+    lo, hi = sharding.shard_range(n_global, rank, world)  # contiguous slice, all starts together
+    seed = instances.BASE_SEED + 4 + 1000 * rank          # each rank generates its own slice
+    P = instances.generate(dims, hi - lo, seed=seed)
     U0 = instances.multistart_guesses(dims, P, starts, seed)
-    B = args.scenarios * starts
+    B = (hi - lo) * starts
     solver = BatchedSolver(dims, robot, cfg, device=dev)
     P_h = torch.from_numpy(P).pin_memory()
     U0_h = torch.from_numpy(U0).pin_memory()
@@ -184,9 +188,13 @@ def main():
         solver.run_batch(P_d, U0_d, starts=starts, out=out)
 
     def step_e2e():
+        # host buffers in, host buffers out; the only inter-GPU traffic of the whole job is
+        # the final gather of the best-of-starts solutions
         Pd = P_h.to(dev, non_blocking=True)
         Ud = U0_h.to(dev, non_blocking=True)
         o = solver.run_batch(Pd, Ud, starts=starts, out=out)
+        bc, bu, bs, _ = sharding.best_of_starts(o["cost"], o["u"], o["exit_status"], starts)
+        sharding.gather_results({"u": bu, "cost": bc, "exit_status": bs}, n_global)
         u_h.copy_(o["u"], non_blocking=True)
         cost_h.copy_(o["cost"], non_blocking=True)
         st_h.copy_(o["exit_status"], non_blocking=True)
@@ -254,8 +262,23 @@ def main():
                      "hbm_algorithmic_gbs": (B * 8 * (dims.np / starts + 2 * dims.nu_total + 10)) / kernel_s / 1e9},
         "solve_stats": stats,
     }
+    if args.latency_solves > 0:
+        # BASELINE configs[1]: one solve per call through the drop-in `solver().run(p)`, host lists
+        from dyobav_mpcnwta_warehouse_b200.solver import solver as make_solver
+        s1 = make_solver(dims, robot, cfg)
+        wall, dev_ms = [], []
+        for i in range(min(args.latency_solves, P.shape[0])):
+            row = P[i].tolist()
+            t0 = time.perf_counter()
+            r = s1.run(row)
+            wall.append(1e3 * (time.perf_counter() - t0))
+            dev_ms.append(r.solve_time_ms)
+        line["latency"] = {"p50_ms": float(np.percentile(wall, 50)), "p95_ms": float(np.percentile(wall, 95)),
+                           "p50_device_ms": float(np.percentile(dev_ms, 50)), "solves": len(wall),
+                           "what": "wall clock of solver().run(p) incl. H2D/D2H, one instance per call, "
+                                   "reference settings (no wall-clock cap)"}
     if not args.no_cpu and world >= 1:
-        n_cpu = args.cpu_solves or max(16, 2 * cores)
+        n_cpu = args.cpu_solves or max(16, 24 * cores)
         v, n, dt, _, _ = cpu_baseline(dims, robot, cfg, P, U0, starts, n_cpu, cores)
         line["cpu_baseline"] = {"value": v, "unit": "solves/s", "cores": cores, "kind": "port",
                                 "sample": f"first {n} solves of rank 0's batch, {dt:.1f} s wall, "

@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(256) solve_kernel(const KParams P, const doubl
         if (b < P.B) {
             const int sc = b / P.starts;
             const double* S = SMEM ? scn + (size_t)(sc - sc0) * P.L.total : staged + (size_t)sc * P.L.total;
-            solve_instance<SPL>(P, S, lb, b, lane, io);
+            solve_worker<SPL, 0>(P, S, nullptr, nullptr, lb, b, lane, io);
         }
     }
 }
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(256) solve_kernel(const KParams P, const doubl
 // K1 (queue variant): every warp pulls its own next instance from the atomic queue, so a
 // slow instance never holds other warps at a CTA barrier; scenario blocks are read from the
 // staged copy in global memory (L1/L2-resident: with culling a solve touches a few KB of it).
-template <int SPL>
+template <int SPL, int MODE>
 __global__ void __launch_bounds__(256, MPCB_MIN_CTAS) solve_kernel_queue(const KParams P, const double* __restrict__ staged,
                                                           const SolveIO io, int* __restrict__ counter)
 {
@@ -381,14 +381,7 @@ __global__ void __launch_bounds__(256, MPCB_MIN_CTAS) solve_kernel_queue(const K
     double* lb_all = reinterpret_cast<double*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* lb = lb_all + (size_t)warp * P.lb_doubles;
-    for (;;) {
-        int b = 0;
-        if (lane == 0) b = atomicAdd(counter, 1);
-        b = __shfl_sync(FULL, b, 0);
-        if (b >= P.B) break;
-        const double* S = staged + (size_t)(b / P.starts) * P.L.total;
-        solve_instance<SPL>(P, S, lb, b, lane, io);
-    }
+    solve_worker<SPL, MODE>(P, nullptr, staged, counter, lb, 0, lane, io);
 }
 
 // ------------------------------------------------------------------ host side
@@ -648,21 +641,22 @@ int32_t mpcb_solve_f64(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solve
         if (grid > ngroups) grid = ngroups;                                                        \
         solve_kernel<SPL, SM><<<grid, threads, pl.smem_bytes, st>>>(pl.P, staged, io, counter);    \
     } while (0)
-#define LAUNCH_QUEUE(SPL)                                                                          \
+#define LAUNCH_QUEUE(SPL, MD)                                                                      \
     do {                                                                                           \
-        rc = set_smem(solve_kernel_queue<SPL>, pl.smem_bytes);                                     \
+        rc = set_smem(solve_kernel_queue<SPL, MD>, pl.smem_bytes);                                 \
         if (rc) return rc;                                                                         \
         int per_sm = 0;                                                                            \
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_kernel_queue<SPL>,   \
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_kernel_queue<SPL, MD>, \
                                                                threads, pl.smem_bytes));           \
         if (per_sm < 1) per_sm = 1;                                                                \
         if (env_int("MPCB_CTAS_PER_SM", 0) > 0) per_sm = env_int("MPCB_CTAS_PER_SM", 0);           \
         int grid = sms * per_sm;                                                                   \
         if (grid > ngroups) grid = ngroups;                                                        \
-        solve_kernel_queue<SPL><<<grid, threads, pl.smem_bytes, st>>>(pl.P, staged, io, counter);  \
+        solve_kernel_queue<SPL, MD><<<grid, threads, pl.smem_bytes, st>>>(pl.P, staged, io, counter); \
     } while (0)
     if (pl.smem) { if (pl.spl == 1) LAUNCH_SOLVE(1, true); else LAUNCH_SOLVE(2, true); }
-    else         { if (pl.spl == 1) LAUNCH_QUEUE(1); else LAUNCH_QUEUE(2); }
+    else if (env_int("MPCB_PHASE_SYNC", 0)) { if (pl.spl == 1) LAUNCH_QUEUE(1, 2); else LAUNCH_QUEUE(2, 2); }
+    else         { if (pl.spl == 1) LAUNCH_QUEUE(1, 1); else LAUNCH_QUEUE(2, 1); }
 #undef LAUNCH_SOLVE
 #undef LAUNCH_QUEUE
     CUDA_TRY(cudaGetLastError());

@@ -200,10 +200,17 @@ struct SolveIO {
 // to evaluate.
 enum EvalFor { ST_INIT, ST_INIT_LIP, ST_LIP_HALF, ST_LIP_U0, ST_LIP_LOOP, ST_NOLS, ST_LS, ST_ALM };
 
-// AlmOptimizer::solve + PANOCOptimizer::solve + PANOCEngine::{init,step} for instance b.
-template <int SPL>
-__device__ __forceinline__ void solve_instance(const KParams& P, const double* __restrict__ S,
-                                               double* lb_mem, int b, int lane, const SolveIO& io)
+// AlmOptimizer::solve + PANOCOptimizer::solve + PANOCEngine::{init,step}.
+//   MODE 0: solve the one instance b0 whose scenario block is S0, then return.
+//   MODE 1: queue worker — pull instances from `counter` until the batch is exhausted.
+//   MODE 2: queue worker whose evaluations are phase-aligned across the CTA: every warp
+//           meets at a barrier before each horizon evaluation, so the warps of an SM run the
+//           same code region at the same time (instruction-cache locality); warps that ran
+//           out of work keep the barrier matched until all are idle.
+template <int SPL, int MODE>
+__device__ __forceinline__ void solve_worker(const KParams& P, const double* __restrict__ S0,
+                                             const double* __restrict__ staged, int* __restrict__ counter,
+                                             double* lb_mem, int b0, int lane, const SolveIO& io)
 {
     const int N = P.L.N;
     bool act[SPL];
@@ -211,6 +218,32 @@ __device__ __forceinline__ void solve_instance(const KParams& P, const double* _
     Inst<SPL> I;
     Lbfgs<SPL> B;
     B.bind(lb_mem, N, P.mem);
+    const double* __restrict__ S = S0;
+    int b = b0;
+
+    double yp_a[SPL], yp_w[SPL];
+    double pt0[SPL], pt1[SPL];          // the point of the pending evaluation
+    double dy = 0.0, dy_plus = 0.0, f2n = 0.0, f2n_plus = 0.0, last_fpr = -1.0, fcost = 0.0;
+    double cost_half = 0.0, rhs_ls = 0.0, tau = 1.0, ceff = 0.0;
+    int alm_iter = 0, n_outer = 0, inner_total = 0, outer = 1;
+    int num_iter = 0, it_lip = 0, ls = 0, inner = MPCB_CONVERGED;
+    int status = MPCB_CONVERGED;
+    int st = ST_INIT;
+    bool cont = true, flag = true, want_grad = true, failed = false;
+    const double EPS = 2.220446049250313e-16;
+    EvalOut<SPL> o;
+
+L_fetch:
+    if (MODE != 0) {
+        int nb = 0;
+        if (lane == 0) nb = atomicAdd(counter, 1);
+        b = __shfl_sync(FULL, nb, 0);
+        if (b >= P.B) {
+            if (MODE == 2) { while (__syncthreads_or(0)) {} }
+            return;
+        }
+        S = staged + (size_t)(b / P.starts) * P.L.total;
+    }
     I.n_cost = 0; I.n_grad = 0;
     MPCB_FORJ {
         const int k = lane + 32 * j;
@@ -218,6 +251,7 @@ __device__ __forceinline__ void solve_instance(const KParams& P, const double* _
         I.gp0[j] = 0.0; I.gp1[j] = 0.0; I.g0[j] = 0.0; I.g1[j] = 0.0;
         I.h0[j] = 0.0; I.h1[j] = 0.0; I.r0[j] = 0.0; I.r1[j] = 0.0;
         I.d0[j] = 0.0; I.d1[j] = 0.0; I.s0[j] = 0.0; I.s1[j] = 0.0;
+        yp_a[j] = 0.0; yp_w[j] = 0.0; pt0[j] = 0.0; pt1[j] = 0.0;
         if (act[j]) {
             if (io.u0) {
                 const double2 t = reinterpret_cast<const double2*>(io.u0 + (size_t)b * 2 * N)[k];
@@ -229,22 +263,12 @@ __device__ __forceinline__ void solve_instance(const KParams& P, const double* _
             }
         }
     }
+    dy = 0.0; dy_plus = 0.0; f2n = 0.0; f2n_plus = 0.0; last_fpr = -1.0; fcost = 0.0;
+    alm_iter = 0; n_outer = 0; inner_total = 0; outer = 1;
+    status = MPCB_CONVERGED; failed = false;
     I.c = io.c0 ? io.c0[b] : P.c_init;
     I.akkt_tol = P.tol0;
     I.gamma = 0.0; I.sigma = 0.0; I.Lc = 0.0; I.cost = 0.0; I.norm_r = 0.0; I.iter = 0;
-
-    double yp_a[SPL], yp_w[SPL];
-    double pt0[SPL], pt1[SPL];          // the point of the pending evaluation
-    MPCB_FORJ { yp_a[j] = 0.0; yp_w[j] = 0.0; pt0[j] = 0.0; pt1[j] = 0.0; }
-    double dy = 0.0, dy_plus = 0.0, f2n = 0.0, f2n_plus = 0.0, last_fpr = -1.0, fcost = 0.0;
-    double cost_half = 0.0, rhs_ls = 0.0, tau = 1.0, ceff = 0.0;
-    int alm_iter = 0, n_outer = 0, inner_total = 0, outer = 1;
-    int num_iter = 0, it_lip = 0, ls = 0, inner = MPCB_CONVERGED;
-    int status = MPCB_CONVERGED;
-    int st = ST_INIT;
-    bool cont = true, flag = true, want_grad = true, failed = false;
-    const double EPS = 2.220446049250313e-16;
-    EvalOut<SPL> o;
 
 L_outer_begin:   // ---- AlmOptimizer::step: project y on Y, then the inner problem
     ++n_outer;
@@ -260,6 +284,7 @@ L_outer_begin:   // ---- AlmOptimizer::step: project y on Y, then the inner prob
     want_grad = true; ceff = I.c; st = ST_INIT;
 
 L_eval:
+    if (MODE == 2) __syncthreads_or(1);
     eval_psi<SPL>(P, S, pt0, pt1, ceff, I.ya, I.yw, want_grad, o, lane);
     if (want_grad) I.n_grad++; else I.n_cost++;
     switch (st) {
@@ -490,6 +515,7 @@ L_finish:
         if (io.penalty) io.penalty[b] = I.c;
         if (io.evals) { io.evals[2 * b] = I.n_cost; io.evals[2 * b + 1] = I.n_grad; }
     }
+    if (MODE != 0) goto L_fetch;
 }
 
 }  // namespace mpcb
