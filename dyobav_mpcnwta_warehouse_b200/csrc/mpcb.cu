@@ -22,6 +22,9 @@
 #include "mpcb_device.cuh"
 #include "mpcb_solver.cuh"
 
+#ifndef MPCB_QTHREADS
+#define MPCB_QTHREADS 256
+#endif
 #ifndef MPCB_MIN_CTAS
 #define MPCB_MIN_CTAS 1
 #endif
@@ -308,7 +311,7 @@ __global__ void __launch_bounds__(256) eval_kernel(const KParams P, const double
     const double cc = c ? c[b] : P.c_init;
     const int n2 = P.L.Ndyn > 0 ? P.L.Ndyn : 1;
     EvalOut<SPL> o;
-    eval_psi<SPL>(P, S, v, w, cc, ya, yw, true, o, lane, F2 ? F2 + (size_t)b * n2 : nullptr);
+    eval_psi<SPL, false>(P, S, v, w, cc, ya, yw, true, o, lane, F2 ? F2 + (size_t)b * n2 : nullptr);
     if (lane == 0) {
         if (f) f[b] = o.f;
         if (psi) psi[b] = o.psi;
@@ -365,7 +368,7 @@ __global__ void __launch_bounds__(256) solve_kernel(const KParams P, const doubl
         if (b < P.B) {
             const int sc = b / P.starts;
             const double* S = SMEM ? scn + (size_t)(sc - sc0) * P.L.total : staged + (size_t)sc * P.L.total;
-            solve_worker<SPL, 0>(P, S, nullptr, nullptr, lb, b, lane, io);
+            solve_worker<SPL, 0, false>(P, S, nullptr, nullptr, lb, b, lane, io);
         }
     }
 }
@@ -373,15 +376,15 @@ __global__ void __launch_bounds__(256) solve_kernel(const KParams P, const doubl
 // K1 (queue variant): every warp pulls its own next instance from the atomic queue, so a
 // slow instance never holds other warps at a CTA barrier; scenario blocks are read from the
 // staged copy in global memory (L1/L2-resident: with culling a solve touches a few KB of it).
-template <int SPL, int MODE>
-__global__ void __launch_bounds__(256, MPCB_MIN_CTAS) solve_kernel_queue(const KParams P, const double* __restrict__ staged,
+template <int SPL, bool FIXED>
+__global__ void __launch_bounds__(MPCB_QTHREADS, MPCB_MIN_CTAS) solve_kernel_queue(const KParams P, const double* __restrict__ staged,
                                                           const SolveIO io, int* __restrict__ counter)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* lb_all = reinterpret_cast<double*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* lb = lb_all + (size_t)warp * P.lb_doubles;
-    solve_worker<SPL, MODE>(P, nullptr, staged, counter, lb, 0, lane, io);
+    solve_worker<SPL, 1, FIXED>(P, nullptr, staged, counter, lb, 0, lane, io);
 }
 
 // ------------------------------------------------------------------ host side
@@ -391,43 +394,7 @@ int build_layout(const mpcb_dims* d, Lay& L)
     if (d->N < 1 || d->N > MPCB_MAX_N || d->nedge < 1 || d->nedge > MPCB_MAX_EDGE || d->Nother < 0 ||
         d->Nstc < 0 || d->Ndyn < 0)
         return MPCB_E_DIMS;
-    const int N = d->N;
-    L.N = N; L.Nother = d->Nother; L.Nstc = d->Nstc; L.nedge = d->nedge; L.Ndyn = d->Ndyn;
-    int o = 0;
-    L.o_hdr = o;  o += H_SIZE;
-    L.o_rv = o;   o += N;
-    L.o_qstc = o; o += N;
-    L.o_seg = o;  o += 5 * N;
-    L.o_c0 = o;   o += 2 * d->Nother;
-    L.o_c = o;    o += 2 * d->Nother * N;
-    L.o_poly = o; o += 3 * d->nedge * d->Nstc;
-    L.o_e0 = o;   o += EF * d->Ndyn;
-    L.o_et = o;   o += EF * d->Ndyn * N;
-    L.o_mg = o;
-    int fo = 0;
-    L.f_e0 = fo;   fo += d->Ndyn * N;
-    L.f_et = fo;   fo += d->Ndyn * N;
-    L.f_poly = fo; fo += d->Nstc * N;
-    L.f_c0 = fo;   fo += d->Nother * N;
-    L.f_c = fo;    fo += d->Nother * N;
-    L.f_imin = fo; fo += d->Ndyn + d->Nstc + 2 * d->Nother;
-    L.f_seg = fo;  fo += N * N;
-    o += (fo + 1) / 2;
-    L.total = (o + 1) & ~1;
-    int q = 0;
-    L.p_um1 = q; q += 2;
-    L.p_s0 = q;  q += 3;
-    L.p_sN = q;  q += 3;
-    L.p_q = q;   q += 10;
-    L.p_rs = q;  q += 3 * N;
-    L.p_rv = q;  q += N;
-    L.p_c0 = q;  q += 3 * d->Nother;
-    L.p_c = q;   q += 3 * N * d->Nother;
-    L.p_os = q;  q += 3 * d->nedge * d->Nstc;
-    L.p_od = q;  q += 6 * (N + 1) * d->Ndyn;
-    L.p_qstc = q; q += N;
-    L.p_qdyn = q; q += N;
-    L.np = q;
+    L = make_lay(d->N, d->Nother, d->Nstc, d->nedge, d->Ndyn);
     return MPCB_OK;
 }
 
@@ -655,8 +622,15 @@ int32_t mpcb_solve_f64(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solve
         solve_kernel_queue<SPL, MD><<<grid, threads, pl.smem_bytes, st>>>(pl.P, staged, io, counter); \
     } while (0)
     if (pl.smem) { if (pl.spl == 1) LAUNCH_SOLVE(1, true); else LAUNCH_SOLVE(2, true); }
-    else if (env_int("MPCB_PHASE_SYNC", 0)) { if (pl.spl == 1) LAUNCH_QUEUE(1, 2); else LAUNCH_QUEUE(2, 2); }
-    else         { if (pl.spl == 1) LAUNCH_QUEUE(1, 1); else LAUNCH_QUEUE(2, 1); }
+    else {
+        constexpr Lay FX = make_lay(MPCB_FIX_DIMS);
+        const bool fixed = env_int("MPCB_FIXED", 1) && d->N == FX.N && d->Nother == FX.Nother &&
+                           d->Nstc == FX.Nstc && d->nedge == FX.nedge && d->Ndyn == FX.Ndyn &&
+                           c->lbfgs_mem == MPCB_FIX_MEM;
+        if (fixed) LAUNCH_QUEUE(1, true);
+        else if (pl.spl == 1) LAUNCH_QUEUE(1, false);
+        else LAUNCH_QUEUE(2, false);
+    }
 #undef LAUNCH_SOLVE
 #undef LAUNCH_QUEUE
     CUDA_TRY(cudaGetLastError());

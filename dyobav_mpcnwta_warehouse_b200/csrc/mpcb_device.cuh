@@ -74,6 +74,71 @@ struct KParams {
     int cull;            // 1: skip provably-zero obstacle terms
 };
 
+// One definition of the staged-block layout, usable at compile time (default dims are
+// constant-folded into the kernel) and at run time (any dims).
+__host__ __device__ constexpr Lay make_lay(int N, int Nother, int Nstc, int nedge, int Ndyn)
+{
+    Lay L{};
+    L.N = N; L.Nother = Nother; L.Nstc = Nstc; L.nedge = nedge; L.Ndyn = Ndyn;
+    int o = 0;
+    L.o_hdr = o;  o += H_SIZE;
+    L.o_rv = o;   o += N;
+    L.o_qstc = o; o += N;
+    L.o_seg = o;  o += 5 * N;
+    L.o_c0 = o;   o += 2 * Nother;
+    L.o_c = o;    o += 2 * Nother * N;
+    L.o_poly = o; o += 3 * nedge * Nstc;
+    L.o_e0 = o;   o += EF * Ndyn;
+    L.o_et = o;   o += EF * Ndyn * N;
+    L.o_mg = o;
+    int fo = 0;
+    L.f_e0 = fo;   fo += Ndyn * N;
+    L.f_et = fo;   fo += Ndyn * N;
+    L.f_poly = fo; fo += Nstc * N;
+    L.f_c0 = fo;   fo += Nother * N;
+    L.f_c = fo;    fo += Nother * N;
+    L.f_imin = fo; fo += Ndyn + Nstc + 2 * Nother;
+    L.f_seg = fo;  fo += N * N;
+    o += (fo + 1) / 2;
+    L.total = (o + 1) & ~1;
+    int q = 0;
+    L.p_um1 = q; q += 2;
+    L.p_s0 = q;  q += 3;
+    L.p_sN = q;  q += 3;
+    L.p_q = q;   q += 10;
+    L.p_rs = q;  q += 3 * N;
+    L.p_rv = q;  q += N;
+    L.p_c0 = q;  q += 3 * Nother;
+    L.p_c = q;   q += 3 * N * Nother;
+    L.p_os = q;  q += 3 * nedge * Nstc;
+    L.p_od = q;  q += 6 * (N + 1) * Ndyn;
+    L.p_qstc = q; q += N;
+    L.p_qdyn = q; q += N;
+    L.np = q;
+    return L;
+}
+
+// the dims of config/mpc_default.yaml / mpc_fast.yaml (lines 21-31): compiled in
+#define MPCB_FIX_DIMS 20, 10, 10, 4, 15
+#define MPCB_FIX_MEM 10
+
+template <bool FIXED>
+struct LayV {
+    const Lay* r;
+#define MPCB_LAYF(name)                                                             \
+    __device__ __forceinline__ int name() const                                     \
+    {                                                                               \
+        if constexpr (FIXED) { constexpr int v = make_lay(MPCB_FIX_DIMS).name; return v; } \
+        else return r->name;                                                        \
+    }
+    MPCB_LAYF(N) MPCB_LAYF(Nother) MPCB_LAYF(Nstc) MPCB_LAYF(nedge) MPCB_LAYF(Ndyn)
+    MPCB_LAYF(o_hdr) MPCB_LAYF(o_rv) MPCB_LAYF(o_qstc) MPCB_LAYF(o_seg) MPCB_LAYF(o_c0) MPCB_LAYF(o_c)
+    MPCB_LAYF(o_poly) MPCB_LAYF(o_e0) MPCB_LAYF(o_et) MPCB_LAYF(o_mg)
+    MPCB_LAYF(f_e0) MPCB_LAYF(f_et) MPCB_LAYF(f_poly) MPCB_LAYF(f_c0) MPCB_LAYF(f_c) MPCB_LAYF(f_imin) MPCB_LAYF(f_seg)
+    MPCB_LAYF(total)
+#undef MPCB_LAYF
+};
+
 // ---------------------------------------------------------------- sin / cos
 // Cody-Waite reduction by pi/2 (two constants, exact first product for
 // |n| < 2^20) + the fdlibm __kernel_sin/__kernel_cos polynomials in Horner
@@ -276,18 +341,18 @@ struct EvalOut {
 #ifndef MPCB_EVAL_ATTR
 #define MPCB_EVAL_ATTR __forceinline__
 #endif
-template <int SPL>
+template <int SPL, bool FIXED>
 __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restrict__ S,
                                          const double (&v)[SPL], const double (&w)[SPL], double c,
                                          const double (&ya)[SPL], const double (&yw)[SPL],
                                          const bool GRAD, EvalOut<SPL>& out, int lane,
                                          double* F2out = nullptr)
 {
-    const Lay& L = P.L;
-    const int N = L.N;
-    const double* H = S + L.o_hdr;
+    const LayV<FIXED> L{&P.L};
+    const int N = L.N();
+    const double* H = S + L.o_hdr();
     const double* q = H + H_Q;
-    const float* MG = reinterpret_cast<const float*>(S + L.o_mg);
+    const float* MG = reinterpret_cast<const float*>(S + L.o_mg());
     const bool CULL = P.cull != 0;
 
     bool act[SPL];
@@ -342,7 +407,7 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
     double X[SPL], Y[SPL];
     float Df[SPL];
     bool anyhinge = false;
-    const double* sg = S + L.o_seg;
+    const double* sg = S + L.o_seg();
 
     // positions and, per step, the distance to the step's anchor (its reference point),
     // inflated and rounded up: every culling test compares a precomputed lower bound with it
@@ -366,10 +431,10 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
         for (int m = 16; m > 0; m >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(FULL, dmax, m));
         if (__any_sync(FULL, bad)) dmax = __int_as_float(0x7f800000);   // non-finite state: cull nothing
     }
-    const float* IM_E = MG + L.f_imin;
-    const float* IM_P = IM_E + L.Ndyn;
-    const float* IM_C0 = IM_P + L.Nstc;
-    const float* IM_C = IM_C0 + L.Nother;
+    const float* IM_E = MG + L.f_imin();
+    const float* IM_P = IM_E + L.Ndyn();
+    const float* IM_C0 = IM_P + L.Nstc();
+    const float* IM_C = IM_C0 + L.Nother();
 
 #pragma unroll
     for (int j = 0; j < SPL; ++j) {
@@ -382,7 +447,7 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
         //    Segments are visited from i = k; the walk stops once the precomputed bound
         //    says no later segment can beat the current minimum.
         {
-            const float* tm = MG + L.f_seg + k * N;
+            const float* tm = MG + L.f_seg() + k * N;
             double best = INFINITY;
             int ib = k;
             bool alive = true;
@@ -420,7 +485,7 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
         }
         // -- speed reference + control effort (mpc_cost.py:46-53,78-79)
         {
-            const double dv = v[j] - S[L.o_rv + k];
+            const double dv = v[j] - S[L.o_rv() + k];
             cst = fma(qvel, dv * dv, cst);
             cst += rv * (v[j] * v[j]) + rw * (w[j] * w[j]);
             gvd[j] = 2.0 * qvel * dv + 2.0 * rv * v[j];
@@ -431,17 +496,17 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
         //    their bits are walked in index order, so sums keep the order of the full loop.
         {
             double s1 = 0.0, s2 = 0.0;
-            const double* c0x = S + L.o_c0;
-            const double* c0y = c0x + L.Nother;
-            const float* m0 = MG + L.f_c0 + k;
-            const double* cx_ = S + L.o_c;
-            const double* cy_ = cx_ + L.Nother * N;
-            const float* m1 = MG + L.f_c + k;
+            const double* c0x = S + L.o_c0();
+            const double* c0y = c0x + L.Nother();
+            const float* m0 = MG + L.f_c0() + k;
+            const double* cx_ = S + L.o_c();
+            const double* cy_ = cx_ + L.Nother() * N;
+            const float* m1 = MG + L.f_c() + k;
 #pragma unroll 1
-            for (int base = 0; base < L.Nother; base += 32) {
+            for (int base = 0; base < L.Nother(); base += 32) {
                 const int it = base + lane;
-                unsigned ma = __ballot_sync(FULL, it >= 1 && it < L.Nother && !(IM_C0[it < L.Nother ? it : 0] > dmax));
-                unsigned mb = __ballot_sync(FULL, it < L.Nother && !(IM_C[it < L.Nother ? it : 0] > dmax));
+                unsigned ma = __ballot_sync(FULL, it >= 1 && it < L.Nother() && !(IM_C0[it < L.Nother() ? it : 0] > dmax));
+                unsigned mb = __ballot_sync(FULL, it < L.Nother() && !(IM_C[it < L.Nother() ? it : 0] > dmax));
                 while (ma) {                              // robot 0 skipped (mpc_builder.py:86-87)
                     const int r = base + __ffs(ma) - 1;
                     ma &= ma - 1;
@@ -471,19 +536,19 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
         // -- static polygons (mpc_builder.py:100-108)
         double sp = 0.0, spx = 0.0, spy = 0.0;
         {
-            const double qs = S[L.o_qstc + k];
-            const double* pe = S + L.o_poly;
-            const float* mp = MG + L.f_poly + k;
+            const double qs = S[L.o_qstc() + k];
+            const double* pe = S + L.o_poly();
+            const float* mp = MG + L.f_poly() + k;
 #pragma unroll 1
-            for (int base = 0; base < L.Nstc; base += 32) {
+            for (int base = 0; base < L.Nstc(); base += 32) {
                 const int it = base + lane;
-                unsigned mk = __ballot_sync(FULL, it < L.Nstc && !(IM_P[it < L.Nstc ? it : 0] > dmax));
+                unsigned mk = __ballot_sync(FULL, it < L.Nstc() && !(IM_P[it < L.Nstc() ? it : 0] > dmax));
                 while (mk) {
                     const int i = base + __ffs(mk) - 1;
                     mk &= mk - 1;
                     if (mp[i * N] > D) continue;
                     double dIx, dIy;
-                    const double I = polygon_ind(GRAD, pe + i * 3 * L.nedge, L.nedge, x, y, dIx, dIy);
+                    const double I = polygon_ind(GRAD, pe + i * 3 * L.nedge(), L.nedge(), x, y, dIx, dIy);
                     if (I > 0.0) {
                         cst = fma(qs, I * I, cst);
                         sp += I;
@@ -501,27 +566,27 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
         // -- dynamic ellipses: t=0 slot (broadcast) and t=k+1 slot (mpc_builder.py:111-143)
         bool hinge = sp > 0.0;
         {
-            const double* e0 = S + L.o_e0;
-            const double* et = S + L.o_et + k;
-            const float* me0 = MG + L.f_e0 + k;
-            const float* met = MG + L.f_et + k;
+            const double* e0 = S + L.o_e0();
+            const double* et = S + L.o_et() + k;
+            const float* me0 = MG + L.f_e0() + k;
+            const float* met = MG + L.f_et() + k;
 #pragma unroll 1
-            for (int base = 0; base < L.Ndyn; base += 32) {
+            for (int base = 0; base < L.Ndyn(); base += 32) {
                 const int it = base + lane;
-                unsigned mk = __ballot_sync(FULL, it < L.Ndyn && !(IM_E[it < L.Ndyn ? it : 0] > dmax));
+                unsigned mk = __ballot_sync(FULL, it < L.Ndyn() && !(IM_E[it < L.Ndyn() ? it : 0] > dmax));
                 while (mk) {
                     const int i = base + __ffs(mk) - 1;
                     mk &= mk - 1;
                     if (!(me0[i * N] > D)) {
                         EllT a;
-                        ellipse_terms(GRAD, e0 + i, L.Ndyn, x, y, a);
+                        ellipse_terms(GRAD, e0 + i, L.Ndyn(), x, y, a);
                         cst += a.cost;
                         if (GRAD) { ggx += a.gx; ggy += a.gy; }
                         hinge |= a.hr > 0.0;
                     }
                     if (!(met[i * N] > D)) {
                         EllT b;
-                        ellipse_terms(GRAD, et + i * N, L.Ndyn * N, x, y, b);
+                        ellipse_terms(GRAD, et + i * N, L.Ndyn() * N, x, y, b);
                         cst += b.cost;
                         if (GRAD) { ggx += b.gx; ggy += b.gy; }
                         hinge |= b.hr > 0.0;
@@ -562,16 +627,16 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
         for (int j = 0; j < SPL; ++j) spl += Spoly[j];
         const double SP = warp_sum(spl);
         double sumF2 = 0.0;
-        if (L.Ndyn == 0) {
+        if (L.Ndyn() == 0) {
             f2sq = SP * SP;
             sumF2 = SP;
             if (F2out && lane == 0) F2out[0] = SP;
         }
 #pragma unroll 1
-        for (int base = 0; base < L.Ndyn; base += 32) {
+        for (int base = 0; base < L.Ndyn(); base += 32) {
             const int it = base + lane;
-            const unsigned mk = __ballot_sync(FULL, it < L.Ndyn && !(IM_E[it < L.Ndyn ? it : 0] > dmax));
-            const int lim = L.Ndyn - base < 32 ? L.Ndyn - base : 32;
+            const unsigned mk = __ballot_sync(FULL, it < L.Ndyn() && !(IM_E[it < L.Ndyn() ? it : 0] > dmax));
+            const int lim = L.Ndyn() - base < 32 ? L.Ndyn() - base : 32;
 #pragma unroll 1
             for (int bi = 0; bi < lim; ++bi) {
                 const int i = base + bi;
@@ -584,10 +649,10 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
                     for (int j = 0; j < SPL; ++j) {
                         const int k = act[j] ? kk[j] : N - 1;
                         a[j].hr = 0.0; b[j].hr = 0.0;
-                        if (act[j] && !(MG[L.f_e0 + i * N + k] > Df[j]))
-                            ellipse_terms(GRAD, S + L.o_e0 + i, L.Ndyn, X[j], Y[j], a[j]);
-                        if (act[j] && !(MG[L.f_et + i * N + k] > Df[j]))
-                            ellipse_terms(GRAD, S + L.o_et + k + i * N, L.Ndyn * N, X[j], Y[j], b[j]);
+                        if (act[j] && !(MG[L.f_e0() + i * N + k] > Df[j]))
+                            ellipse_terms(GRAD, S + L.o_e0() + i, L.Ndyn(), X[j], Y[j], a[j]);
+                        if (act[j] && !(MG[L.f_et() + i * N + k] > Df[j]))
+                            ellipse_terms(GRAD, S + L.o_et() + k + i * N, L.Ndyn() * N, X[j], Y[j], b[j]);
                         hl += a[j].hr + b[j].hr;
                     }
                     if (__any_sync(FULL, hl > 0.0)) F2i += warp_sum(hl);

@@ -207,17 +207,18 @@ enum EvalFor { ST_INIT, ST_INIT_LIP, ST_LIP_HALF, ST_LIP_U0, ST_LIP_LOOP, ST_NOL
 //           meets at a barrier before each horizon evaluation, so the warps of an SM run the
 //           same code region at the same time (instruction-cache locality); warps that ran
 //           out of work keep the barrier matched until all are idle.
-template <int SPL, int MODE>
+template <int SPL, int MODE, bool FIXED>
 __device__ __forceinline__ void solve_worker(const KParams& P, const double* __restrict__ S0,
                                              const double* __restrict__ staged, int* __restrict__ counter,
                                              double* lb_mem, int b0, int lane, const SolveIO& io)
 {
-    const int N = P.L.N;
+    const LayV<FIXED> LV{&P.L};
+    const int N = LV.N();
     bool act[SPL];
     MPCB_FORJ act[j] = lane + 32 * j < N;
     Inst<SPL> I;
     Lbfgs<SPL> B;
-    B.bind(lb_mem, N, P.mem);
+    B.bind(lb_mem, N, FIXED ? MPCB_FIX_MEM : P.mem);
     const double* __restrict__ S = S0;
     int b = b0;
 
@@ -242,7 +243,7 @@ L_fetch:
             if (MODE == 2) { while (__syncthreads_or(0)) {} }
             return;
         }
-        S = staged + (size_t)(b / P.starts) * P.L.total;
+        S = staged + (size_t)(b / P.starts) * LV.total();
     }
     I.n_cost = 0; I.n_grad = 0;
     MPCB_FORJ {
@@ -285,7 +286,7 @@ L_outer_begin:   // ---- AlmOptimizer::step: project y on Y, then the inner prob
 
 L_eval:
     if (MODE == 2) __syncthreads_or(1);
-    eval_psi<SPL>(P, S, pt0, pt1, ceff, I.ya, I.yw, want_grad, o, lane);
+    eval_psi<SPL, FIXED>(P, S, pt0, pt1, ceff, I.ya, I.yw, want_grad, o, lane);
     if (want_grad) I.n_grad++; else I.n_cost++;
     switch (st) {
         case ST_INIT: goto H_INIT;
@@ -461,7 +462,7 @@ H_ALM: {
     f2n_plus = sqrt(o.f2sq);
     // update_lagrange_multipliers: y+ = y + c (F1 - Proj_C(F1 + y/c))
     double dsum = 0.0;
-    double vc = S[P.L.o_hdr + H_UM1V], wc = S[P.L.o_hdr + H_UM1W];
+    double vc = S[LV.o_hdr() + H_UM1V], wc = S[LV.o_hdr() + H_UM1W];
     MPCB_FORJ {
         double vp = __shfl_up_sync(FULL, I.u0[j], 1), wp = __shfl_up_sync(FULL, I.u1[j], 1);
         if (lane == 0) { vp = vc; wp = wc; }
