@@ -25,6 +25,9 @@
 #ifndef MPCB_QTHREADS
 #define MPCB_QTHREADS 256
 #endif
+#ifndef MPCB_QTHREADS_FIXED
+#define MPCB_QTHREADS_FIXED 384   // 12 warps x 168 registers: best measured for the default dims
+#endif
 #ifndef MPCB_MIN_CTAS
 #define MPCB_MIN_CTAS 1
 #endif
@@ -377,7 +380,7 @@ __global__ void __launch_bounds__(256) solve_kernel(const KParams P, const doubl
 // slow instance never holds other warps at a CTA barrier; scenario blocks are read from the
 // staged copy in global memory (L1/L2-resident: with culling a solve touches a few KB of it).
 template <int SPL, bool FIXED>
-__global__ void __launch_bounds__(MPCB_QTHREADS, MPCB_MIN_CTAS) solve_kernel_queue(const KParams P, const double* __restrict__ staged,
+__global__ void __launch_bounds__(FIXED ? MPCB_QTHREADS_FIXED : MPCB_QTHREADS, MPCB_MIN_CTAS) solve_kernel_queue(const KParams P, const double* __restrict__ staged,
                                                           const SolveIO io, int* __restrict__ counter)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -409,6 +412,7 @@ constexpr size_t WS_HEADER = 256;   // bytes reserved for the work-queue counter
 struct Plan {
     KParams P;
     bool smem;
+    bool fixed;
     int spl;
     size_t smem_bytes;
 };
@@ -449,6 +453,7 @@ int make_plan(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solver_cfg* c,
     const size_t cap = 227 * 1024;
     const size_t blk = (size_t)P.L.total * 8, lbw = (size_t)P.lb_doubles * 8;
     pl.smem = false;
+    pl.fixed = false;
     int best_wps = 0;
     for (int W = 8; W >= 1; W >>= 1) {
         int nsc;
@@ -469,8 +474,12 @@ int make_plan(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solver_cfg* c,
     if (best_wps < 8 || (mode != 1 && need_lbfgs)) {
         // queue variant (solve) / too few resident warps: read the staged blocks through L1/L2
         pl.smem = false;
-        P.warps = env_int("MPCB_WARPS", 8); P.nsc = 0;
-        if (P.warps < 1 || P.warps > 8) P.warps = 8;
+        constexpr Lay FXD = make_lay(MPCB_FIX_DIMS);
+        pl.fixed = need_lbfgs && env_int("MPCB_FIXED", 1) && d->N == FXD.N && d->Nother == FXD.Nother &&
+                   d->Nstc == FXD.Nstc && d->nedge == FXD.nedge && d->Ndyn == FXD.Ndyn &&
+                   c->lbfgs_mem == MPCB_FIX_MEM;
+        P.warps = env_int("MPCB_WARPS", pl.fixed ? MPCB_QTHREADS_FIXED / 32 : MPCB_QTHREADS / 32); P.nsc = 0;
+        if (P.warps < 1 || P.warps > (pl.fixed ? MPCB_QTHREADS_FIXED : MPCB_QTHREADS) / 32) P.warps = 8;
         pl.smem_bytes = 16 + P.warps * lbw;
     }
     return MPCB_OK;
@@ -623,11 +632,7 @@ int32_t mpcb_solve_f64(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solve
     } while (0)
     if (pl.smem) { if (pl.spl == 1) LAUNCH_SOLVE(1, true); else LAUNCH_SOLVE(2, true); }
     else {
-        constexpr Lay FX = make_lay(MPCB_FIX_DIMS);
-        const bool fixed = env_int("MPCB_FIXED", 1) && d->N == FX.N && d->Nother == FX.Nother &&
-                           d->Nstc == FX.Nstc && d->nedge == FX.nedge && d->Ndyn == FX.Ndyn &&
-                           c->lbfgs_mem == MPCB_FIX_MEM;
-        if (fixed) LAUNCH_QUEUE(1, true);
+        if (pl.fixed) LAUNCH_QUEUE(1, true);
         else if (pl.spl == 1) LAUNCH_QUEUE(1, false);
         else LAUNCH_QUEUE(2, false);
     }
