@@ -1,0 +1,106 @@
+"""Closed loop (north_star "closed-loop trajectories"): the receding-horizon
+harness driven by the CPU oracles (CPU test) and by the GPU solver vs the laned oracle (GPU)."""
+import copy
+import os
+
+import numpy as np
+import pytest
+
+from dyobav_mpcnwta_warehouse_b200 import Dims, MpcConfig, RobotSpec, SolverSettings
+from dyobav_mpcnwta_warehouse_b200.closed_loop import ClosedLoopBatch, Episode, make_episodes, unicycle_rk4
+from oracle import oracle
+
+CFG = SolverSettings(max_inner=150, max_outer=4)     # iteration budget stands in for the 0.1 s cap
+
+
+def _oracle_solve(laned):
+    def solve(P):
+        U, SC = oracle.solve_batch(Dims(), RobotSpec(), CFG, P, None, threads=os.cpu_count(), laned=laned)
+        return U, SC[:, 0], SC[:, 9].astype(np.int32)
+    return solve
+
+
+def test_unicycle_rk4_matches_oracle_rollout():
+    import ctypes
+    s = np.array([0.3, -0.2, 0.4])
+    out = (ctypes.c_double * 3)()
+    oracle.lib().mpco_unicycle_rk4((ctypes.c_double * 3)(*s), 1.1, 0.35, 0.2, out)
+    np.testing.assert_allclose(unicycle_rk4(s, np.array([1.1, 0.35]), 0.2), list(out), rtol=0, atol=1e-15)
+
+
+def test_robot_reaches_goal_on_free_straight_path():
+    ep = Episode(np.array([0.0, 5.0, 0.0]) + np.array([3.0, 0.0, 0.0]), [(9.0, 5.0)])
+    sim = ClosedLoopBatch(Dims(), MpcConfig(), [ep], _oracle_solve(False))
+    sim.run(60)
+    assert ep.done, (ep.states[-1], len(ep.states))
+    xs = np.array(ep.states)
+    assert np.abs(xs[:, 1] - 5.0).max() < 0.05          # stays on the line
+    v = np.array(ep.actions)[:, 0]
+    assert (np.diff(np.concatenate([[0.0], v])) <= 1.0 * 0.2 + 0.1).all()    # acceleration bound: soft (ALM, iteration budget)
+    assert v.max() <= 1.5 + 1e-9 and v.max() > 1.0      # speeds up to about the reference speed
+
+
+def test_closed_loop_avoids_pedestrians_and_rectangles():
+    eps = make_episodes(4, seed=11)
+    sim = ClosedLoopBatch(Dims(), MpcConfig(), eps, _oracle_solve(True))
+    sim.run(25)
+    for e in eps:
+        xs = np.array(e.states)[:, :2]
+        assert np.isfinite(xs).all()
+        for poly in e.polygons:                          # never inside an (inflated) rectangle
+            lo, hi = poly.min(0), poly.max(0)
+            inside = ((xs > lo + 0.05) & (xs < hi - 0.05)).all(1)
+            assert not inside.any()
+
+
+@pytest.mark.gpu
+def test_gpu_closed_loop_equals_laned_oracle_bitwise():
+    """Same closed loop, GPU solver vs laned oracle: every state of every episode identical."""
+    import torch
+    from dyobav_mpcnwta_warehouse_b200.solver import BatchedSolver
+    bs = BatchedSolver(Dims(), RobotSpec(), CFG)
+
+    def gpu_solve(P):
+        o = bs.run_batch(torch.as_tensor(P, device="cuda"))
+        torch.cuda.synchronize()
+        return o["u"].cpu().numpy(), o["cost"].cpu().numpy(), o["exit_status"].cpu().numpy()
+
+    eps_a = make_episodes(12, seed=5)
+    eps_b = copy.deepcopy(eps_a)
+    a = ClosedLoopBatch(Dims(), MpcConfig(), eps_a, gpu_solve)
+    b = ClosedLoopBatch(Dims(), MpcConfig(), eps_b, _oracle_solve(True))
+    a.run(20)
+    b.run(20)
+    for ea, eb in zip(eps_a, eps_b):
+        np.testing.assert_array_equal(np.array(ea.states), np.array(eb.states))
+        np.testing.assert_array_equal(np.array(ea.actions), np.array(eb.actions))
+        assert ea.statuses == eb.statuses and ea.costs == eb.costs
+
+
+@pytest.mark.gpu
+def test_gpu_closed_loop_close_to_reference_order_oracle():
+    """Against the reference-order oracle the closed-loop trajectories stay within a stated
+    tolerance (0.05 m over 15 steps): feedback re-anchors the solve every step, so round-off
+    level differences in the applied input do not accumulate."""
+    import torch
+    from dyobav_mpcnwta_warehouse_b200.solver import BatchedSolver
+    bs = BatchedSolver(Dims(), RobotSpec(), SolverSettings())
+
+    def gpu_solve(P):
+        o = bs.run_batch(torch.as_tensor(P, device="cuda"))
+        torch.cuda.synchronize()
+        return o["u"].cpu().numpy(), o["cost"].cpu().numpy(), o["exit_status"].cpu().numpy()
+
+    def ref_solve(P):
+        U, SC = oracle.solve_batch(Dims(), RobotSpec(), SolverSettings(), P, None, threads=os.cpu_count())
+        return U, SC[:, 0], SC[:, 9].astype(np.int32)
+
+    eps_a = [Episode(np.array([3.0, 5.0, 0.1]), [(9.0, 5.0), (9.0, 9.0)]) for _ in range(2)]
+    eps_b = copy.deepcopy(eps_a)
+    a = ClosedLoopBatch(Dims(), MpcConfig(), eps_a, gpu_solve)
+    b = ClosedLoopBatch(Dims(), MpcConfig(), eps_b, ref_solve)
+    a.run(15)
+    b.run(15)
+    for ea, eb in zip(eps_a, eps_b):
+        n = min(len(ea.states), len(eb.states))
+        assert np.abs(np.array(ea.states[:n]) - np.array(eb.states[:n]))[:, :2].max() < 0.05
