@@ -663,11 +663,21 @@ int32_t mpcb_solve_one_host(const mpcb_dims* d, const mpcb_robot* r, const mpcb_
     const size_t o_p = 0, o_u0 = o_p + (size_t)L.np * 8, o_y0 = o_u0 + (size_t)n * 8,
                  o_c0 = o_y0 + (size_t)n * 8, o_u = o_c0 + 16, o_y = o_u + (size_t)n * 8,
                  o_sc = o_y + (size_t)n * 8, o_i = o_sc + 5 * 8, o_ws = (o_i + 5 * 4 + 255) & ~(size_t)255;
-    char* arena = nullptr;
-    CUDA_TRY(cudaMalloc(&arena, o_ws + ws));
+    // per-thread cached device arena + events: the single-solve path is called once per
+    // control period, so allocation must not be on it
+    static thread_local char* t_arena = nullptr;
+    static thread_local size_t t_arena_bytes = 0;
+    static thread_local cudaEvent_t t_e0 = nullptr, t_e1 = nullptr;
+    if (t_arena_bytes < o_ws + ws) {
+        if (t_arena) cudaFree(t_arena);
+        t_arena = nullptr; t_arena_bytes = 0;
+        CUDA_TRY(cudaMalloc(&t_arena, o_ws + ws));
+        t_arena_bytes = o_ws + ws;
+    }
+    if (!t_e0) { CUDA_TRY(cudaEventCreate(&t_e0)); CUDA_TRY(cudaEventCreate(&t_e1)); }
+    char* arena = t_arena;
     cudaStream_t st = 0;
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEvent_t e0 = t_e0, e1 = t_e1;
     cudaMemcpyAsync(arena + o_p, p_host, (size_t)L.np * 8, cudaMemcpyHostToDevice, st);
     if (u0_host) cudaMemcpyAsync(arena + o_u0, u0_host, (size_t)n * 8, cudaMemcpyHostToDevice, st);
     if (y0_host) cudaMemcpyAsync(arena + o_y0, y0_host, (size_t)n * 8, cudaMemcpyHostToDevice, st);
@@ -693,8 +703,6 @@ int32_t mpcb_solve_one_host(const mpcb_dims* d, const mpcb_robot* r, const mpcb_
     cudaError_t e = cudaStreamSynchronize(st);
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-    cudaFree(arena);
     if (rc) return rc;
     if (e != cudaSuccess) {
         snprintf(g_err, sizeof(g_err), "solve: %s", cudaGetErrorString(e));
