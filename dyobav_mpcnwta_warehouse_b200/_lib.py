@@ -18,7 +18,17 @@ ERRORS = {-1: "unsupported or inconsistent dimensions", -2: "required pointer is
 # every symbol include/mpcb.h declares
 EXPORTS = ("mpcb_abi_version", "mpcb_last_error", "mpcb_param_len", "mpcb_num_decision", "mpcb_n1",
            "mpcb_n2", "mpcb_default_robot", "mpcb_default_solver_cfg", "mpcb_workspace_bytes",
-           "mpcb_eval_f64", "mpcb_solve_f64", "mpcb_solve_one_host")
+           "mpcb_eval_f64", "mpcb_solve_f64", "mpcb_solve_one_host", "mpcb_pack_f64",
+           "mpcb_plant_step_f64", "mpcb_sincos_host")
+
+
+class CSim(ctypes.Structure):
+    """mpcb_sim (include/mpcb.h): device pointers as integers."""
+    _fields_ = ([(n, ctypes.c_int32) for n in ("n", "T", "Kp", "Pd", "M")]
+                + [(n, ctypes.c_double) for n in ("base_speed", "lin_vel_max", "ped_size", "stc_w", "dyn_w", "ts")]
+                + [("tuning", ctypes.c_double * 10)]
+                + [(n, ctypes.c_void_p) for n in ("state", "last_u", "ref_traj", "ref_len", "idx_ref", "goal",
+                                                   "polys", "n_poly", "ped_pos", "ped_vel", "done")])
 
 
 def load():
@@ -48,6 +58,13 @@ def load():
     L.mpcb_solve_f64.argtypes = [pd, pr, pc, i32, i32] + [dp] * 15 + [vp, ctypes.c_size_t, vp]
     L.mpcb_solve_one_host.restype = i32
     L.mpcb_solve_one_host.argtypes = [pd, pr, pc] + [dp] * 8
+    L.mpcb_pack_f64.restype = i32
+    L.mpcb_pack_f64.argtypes = [pd, ctypes.POINTER(CSim), dp, vp]
+    L.mpcb_plant_step_f64.restype = i32
+    L.mpcb_plant_step_f64.argtypes = [pd, ctypes.POINTER(CSim), dp, vp]
+    L.mpcb_sincos_host.restype = None
+    L.mpcb_sincos_host.argtypes = [ctypes.c_double, ctypes.POINTER(ctypes.c_double),
+                                   ctypes.POINTER(ctypes.c_double)]
     _lib = L
     return L
 
@@ -58,3 +75,10 @@ def check(rc: int, what: str):
         if rc == -4 and _lib is not None:
             detail = ": " + _lib.mpcb_last_error().decode(errors="replace")
         raise RuntimeError(f"{what} failed ({rc}: {ERRORS.get(rc, 'unknown error')}{detail})")
+
+
+def sincos_host(x: float):
+    """The kernels' portable sin/cos evaluated on the host (bit-identical to the device)."""
+    sn, cs = ctypes.c_double(), ctypes.c_double()
+    load().mpcb_sincos_host(float(x), ctypes.byref(sn), ctypes.byref(cs))
+    return sn.value, cs.value

@@ -28,10 +28,17 @@ from . import packing
 from .problem import Dims, MpcConfig
 
 
-def unicycle_rk4(state: np.ndarray, action: np.ndarray, ts: float) -> np.ndarray:
-    """The reference's numpy branch of ``unicycle_model`` (motion_model.py:141-163), RK4."""
+def _libm_sincos(x: float):
+    return math.sin(x), math.cos(x)
+
+
+def unicycle_rk4(state: np.ndarray, action: np.ndarray, ts: float, sincos=_libm_sincos) -> np.ndarray:
+    """The reference's numpy branch of ``unicycle_model`` (motion_model.py:141-163), RK4.
+    ``sincos`` defaults to libm; the device plant kernel uses the library's portable routine
+    (``_lib.sincos_host``), which can be passed here to reproduce it bit for bit."""
     def d(s):
-        return ts * np.array([action[0] * math.cos(s[2]), action[0] * math.sin(s[2]), action[1]])
+        sn, cs = sincos(float(s[2]))
+        return ts * np.array([action[0] * cs, action[0] * sn, action[1]])
     k1 = d(state)
     k2 = d(state + 0.5 * k1)
     k3 = d(state + 0.5 * k2)
@@ -65,8 +72,9 @@ class Episode:
 
 class ClosedLoopBatch:
     def __init__(self, dims: Dims, cfg: MpcConfig, episodes: Sequence[Episode],
-                 solve: Callable[[np.ndarray], tuple]):
+                 solve: Callable[[np.ndarray], tuple], sincos=_libm_sincos):
         self.dims, self.cfg, self.eps, self.solve = dims, cfg, list(episodes), solve
+        self.sincos = sincos
         rb = cfg.robot()
         self.ts = rb.ts
         self.base_speed = rb.lin_vel_max * 0.8            # 'work' mode (trajectory_tracker.py:142-143)
@@ -83,7 +91,8 @@ class ClosedLoopBatch:
         d, N = self.dims, self.dims.N
         ref_states, e.idx_ref = packing.ref_states_window(e.idx_ref, e.ref_traj, e.state, 1, N)
         goal = e.ref_path[-1]
-        dist_to_goal = math.hypot(e.state[0] - goal[0], e.state[1] - goal[1])
+        gx, gy = e.state[0] - goal[0], e.state[1] - goal[1]
+        dist_to_goal = math.sqrt(gx * gx + gy * gy)
         if dist_to_goal >= self.base_speed * N * self.ts:
             speed_ref = self.base_speed
         else:                                              # the reference's max() (SURVEY C-8)
@@ -102,7 +111,8 @@ class ClosedLoopBatch:
         # static obstacles: the Nstcobs closest polygons (mpc_interface.py:90-100)
         stc = [0.0] * (d.Nstc * 3 * d.nedge)
         if e.polygons:
-            dist = [float(np.min(np.hypot(*(np.asarray(p) - e.state[:2]).T))) for p in e.polygons]
+            dist = [min(math.sqrt((vx - e.state[0]) * (vx - e.state[0]) + (vy - e.state[1]) * (vy - e.state[1]))
+                        for vx, vy in np.asarray(p)) for p in e.polygons]
             order = np.argsort(dist, kind="stable")[: d.Nstc]
             for slot, i in enumerate(order):
                 b, a0, a1 = e._halfspaces[i]
@@ -120,7 +130,7 @@ class ClosedLoopBatch:
         u, cost, status = self.solve(P)
         for e, ue, ce, se in zip(live, np.asarray(u), np.asarray(cost), np.asarray(status)):
             a = np.array(ue[:2], dtype=np.float64)         # action_steps = 1
-            e.state = unicycle_rk4(e.state, a, self.ts)
+            e.state = unicycle_rk4(e.state, a, self.ts, self.sincos)
             e.last_u = a
             e.states.append(e.state.copy()); e.actions.append(a); e.costs.append(float(ce)); e.statuses.append(int(se))
             for p in e.pedestrians:

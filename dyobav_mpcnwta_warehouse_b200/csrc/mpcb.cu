@@ -21,6 +21,7 @@
 
 #include "mpcb_device.cuh"
 #include "mpcb_solver.cuh"
+#include "mpcb_sim.cuh"
 
 #ifndef MPCB_QTHREADS
 #define MPCB_QTHREADS 256
@@ -714,6 +715,38 @@ int32_t mpcb_solve_one_host(const mpcb_dims* d, const mpcb_robot* r, const mpcb_
         out_scalars[3] = hsc[3]; out_scalars[4] = hsc[4];
         out_scalars[5] = hiv[1]; out_scalars[6] = hiv[2]; out_scalars[7] = ms;
     }
+    return MPCB_OK;
+}
+
+// ---- closed-loop support --------------------------------------------
+void mpcb_sincos_host(double x, double* sn, double* cs) { mpcb::sincos_cw(x, sn, cs); }
+
+int32_t mpcb_pack_f64(const mpcb_dims* d, const mpcb_sim* sim, double* p_out, void* stream)
+{
+    if (!d || !sim || !p_out) return MPCB_E_NULL;
+    Lay L;
+    int rc = build_layout(d, L);
+    if (rc) return rc;
+    if (sim->n < 1 || sim->T < 1 || sim->Kp < 0 || sim->Kp > 64 || sim->Pd < 0 || sim->M < 1) return MPCB_E_DIMS;
+    if (!sim->state || !sim->last_u || !sim->ref_traj || !sim->ref_len || !sim->idx_ref || !sim->goal ||
+        !sim->n_poly || !sim->done || (sim->Kp && !sim->polys) || (sim->Pd && (!sim->ped_pos || !sim->ped_vel)))
+        return MPCB_E_NULL;
+    SimArgs A;
+    static_assert(sizeof(SimArgs) == sizeof(mpcb_sim), "mpcb_sim must mirror SimArgs");
+    memcpy(&A, sim, sizeof(A));
+    pack_kernel<<<sim->n, 64, 0, reinterpret_cast<cudaStream_t>(stream)>>>(L, A, p_out);
+    CUDA_TRY(cudaGetLastError());
+    return MPCB_OK;
+}
+
+int32_t mpcb_plant_step_f64(const mpcb_dims* d, const mpcb_sim* sim, const double* u, void* stream)
+{
+    if (!d || !sim || !u) return MPCB_E_NULL;
+    if (sim->n < 1 || d->N < 1) return MPCB_E_DIMS;
+    SimArgs A;
+    memcpy(&A, sim, sizeof(A));
+    plant_kernel<<<(sim->n + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(A, 2 * d->N, u);
+    CUDA_TRY(cudaGetLastError());
     return MPCB_OK;
 }
 

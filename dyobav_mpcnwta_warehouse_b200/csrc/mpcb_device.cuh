@@ -143,7 +143,7 @@ struct LayV {
 // Cody-Waite reduction by pi/2 (two constants, exact first product for
 // |n| < 2^20) + the fdlibm __kernel_sin/__kernel_cos polynomials in Horner
 // form.  |error| ~ 1 ulp for |x| < 1e5; identical code in the laned oracle.
-__device__ MPCB_HELPER_ATTR void sincos_cw(double x, double* sn, double* cs)
+__host__ __device__ MPCB_HELPER_ATTR void sincos_cw(double x, double* sn, double* cs)
 {
     const double fn = rint(x * 6.36619772367581382433e-01);
     double r = fma(-fn, 1.57079632673412561417e+00, x);

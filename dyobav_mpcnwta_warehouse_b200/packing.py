@@ -132,7 +132,10 @@ def ref_states_window(idx_ref_traj: int, ref_traj, state, action_steps: int = 1,
     """Next ``horizon`` reference states from the closest trajectory sample, padded with the last."""
     lb = max(0, idx_ref_traj - action_steps)
     ub = min(len(ref_traj), idx_ref_traj + 5 * action_steps)
-    dists = [math.hypot(state[0] - r[0], state[1] - r[1]) for r in ref_traj[lb:ub]]
+    # sqrt(dx*dx + dy*dy) instead of the reference's math.hypot (trajectory_tracker.py:257): the
+    # same selection up to last-bit ties, and reproducible bit for bit by the device packer
+    dists = [math.sqrt((state[0] - r[0]) * (state[0] - r[0]) + (state[1] - r[1]) * (state[1] - r[1]))
+             for r in ref_traj[lb:ub]]
     idx = dists.index(min(dists)) + lb
     win = list(ref_traj[idx:idx + horizon])
     while len(win) < horizon:

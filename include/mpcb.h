@@ -177,6 +177,39 @@ int32_t mpcb_solve_one_host(const mpcb_dims* dims, const mpcb_robot* robot,
                             double* u_out_host, double* y_out_host,
                             int32_t* exit_status_host, double* out_scalars);
 
+/* ---- closed-loop support: device-side packer and plant ----------
+ * Episode state for E parallel receding-horizon episodes; every pointer is a DEVICE pointer.
+ * mpcb_pack_f64 writes one reference-layout parameter row per episode, replacing the host
+ * work of TrajectoryTracker.run_step (trajectory_tracker.py:285-317), get_ref_states
+ * (:243-270) and MpcInterface.get_stc_constraints / get_dyn_constraints
+ * (mpc_interface.py:73-100); mpcb_plant_step_f64 applies the first action with the RK4
+ * unicycle (motion_model.py:141-163, basic_agent.py:106), advances the pedestrians and
+ * evaluates the termination test (trajectory_tracker.py:191-199). */
+typedef struct mpcb_sim {
+    int32_t n;              /* episodes                                              */
+    int32_t T;              /* padded length of every reference trajectory           */
+    int32_t Kp;             /* polygon slots per episode (4 vertices each, <= 64)    */
+    int32_t Pd, M;          /* pedestrians per episode, predicted modes each         */
+    double base_speed, lin_vel_max, ped_size, stc_w, dyn_w, ts;
+    double tuning[10];      /* q block (trajectory_tracker.py:138-139)               */
+    double* state;          /* [n,3] in/out                                          */
+    double* last_u;         /* [n,2] in/out                                          */
+    const double* ref_traj; /* [n,T,3]                                               */
+    const int32_t* ref_len; /* [n]                                                   */
+    int32_t* idx_ref;       /* [n] in/out                                            */
+    const double* goal;     /* [n,2]                                                 */
+    const double* polys;    /* [n,Kp,4,2] inflated rectangles/quadrilaterals         */
+    const int32_t* n_poly;  /* [n]                                                   */
+    double* ped_pos;        /* [n,Pd,2] in/out                                       */
+    const double* ped_vel;  /* [n,Pd,M,2]; mode 0 is the motion that happens         */
+    int32_t* done;          /* [n] in/out                                            */
+} mpcb_sim;
+
+int32_t mpcb_pack_f64(const mpcb_dims* dims, const mpcb_sim* sim, double* p_out, void* stream);
+int32_t mpcb_plant_step_f64(const mpcb_dims* dims, const mpcb_sim* sim, const double* u, void* stream);
+/* the portable sin/cos the kernels use, callable on the host (bit-identical) */
+void mpcb_sincos_host(double x, double* sn, double* cs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -104,3 +104,47 @@ def test_gpu_closed_loop_close_to_reference_order_oracle():
     for ea, eb in zip(eps_a, eps_b):
         n = min(len(ea.states), len(eb.states))
         assert np.abs(np.array(ea.states[:n]) - np.array(eb.states[:n]))[:, :2].max() < 0.05
+
+
+@pytest.mark.gpu
+def test_device_packer_row_equals_host_packer_bitwise():
+    """K4 (device-side packer) writes the same parameter rows as the host
+    mirror of the reference's packing code, bit for bit."""
+    import torch
+    from dyobav_mpcnwta_warehouse_b200.closed_loop_gpu import ClosedLoopGPU
+    eps_a = make_episodes(16, seed=2)
+    eps_b = copy.deepcopy(eps_a)
+    g = ClosedLoopGPU(Dims(), MpcConfig(), eps_a, CFG)
+    import ctypes
+    from dyobav_mpcnwta_warehouse_b200 import _lib
+    _lib.check(g.lib.mpcb_pack_f64(ctypes.byref(g._cd), ctypes.byref(g.sim), ctypes.c_void_p(g.P.data_ptr()), None),
+               "pack")
+    torch.cuda.synchronize()
+    h = ClosedLoopBatch(Dims(), MpcConfig(), eps_b, _oracle_solve(True))
+    rows = np.array([h._row(e) for e in eps_b])
+    np.testing.assert_array_equal(g.P.cpu().numpy(), rows)
+
+
+@pytest.mark.gpu
+def test_device_closed_loop_equals_host_closed_loop_bitwise():
+    """pack -> solve -> plant entirely on the GPU for 25 control periods vs the host harness
+    driven by the laned oracle (and the library's portable sin/cos in the plant): identical
+    robot states, reference indices and termination flags."""
+    import torch
+    from dyobav_mpcnwta_warehouse_b200 import _lib
+    from dyobav_mpcnwta_warehouse_b200.closed_loop_gpu import ClosedLoopGPU
+    eps_a = make_episodes(10, seed=4)
+    eps_b = copy.deepcopy(eps_a)
+    g = ClosedLoopGPU(Dims(), MpcConfig(), eps_a, CFG)
+    h = ClosedLoopBatch(Dims(), MpcConfig(), eps_b, _oracle_solve(True), sincos=_lib.sincos_host)
+    steps = 25
+    traj = g.run(steps, record=True)
+    torch.cuda.synchronize()
+    h.run(steps)
+    traj = torch.stack(traj).cpu().numpy()                 # [steps+1, n, 3]
+    for i, e in enumerate(eps_b):
+        hs = np.array(e.states)
+        np.testing.assert_array_equal(traj[:len(hs), i], hs)
+        assert bool(g.done[i].item()) == e.done
+        if not e.done:
+            assert int(g.idx_ref[i].item()) == e.idx_ref
