@@ -396,7 +396,7 @@ int build_layout(const mpcb_dims* d, Lay& L)
 {
     if (!d) return MPCB_E_NULL;
     if (d->N < 1 || d->N > MPCB_MAX_N || d->nedge < 1 || d->nedge > MPCB_MAX_EDGE || d->Nother < 0 ||
-        d->Nstc < 0 || d->Ndyn < 0)
+        d->Nstc < 0 || d->Ndyn < 0 || d->Ndyn > MPCB_MAX_NDYN)
         return MPCB_E_DIMS;
     L = make_lay(d->N, d->Nother, d->Nstc, d->nedge, d->Ndyn);
     return MPCB_OK;

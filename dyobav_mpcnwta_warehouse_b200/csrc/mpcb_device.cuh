@@ -407,6 +407,7 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
     double X[SPL], Y[SPL];
     float Df[SPL];
     bool anyhinge = false;
+    unsigned hm[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};   // obstacles whose raw hinge is positive (Ndyn <= 256)
     const double* sg = S + L.o_seg();
 
     // positions and, per step, the distance to the step's anchor (its reference point),
@@ -575,22 +576,25 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
                 const int it = base + lane;
                 unsigned mk = __ballot_sync(FULL, it < L.Ndyn() && !(IM_E[it < L.Ndyn() ? it : 0] > dmax));
                 while (mk) {
-                    const int i = base + __ffs(mk) - 1;
+                    const int bit = __ffs(mk) - 1;
+                    const int i = base + bit;
                     mk &= mk - 1;
+                    bool hit = false;
                     if (!(me0[i * N] > D)) {
                         EllT a;
                         ellipse_terms(GRAD, e0 + i, L.Ndyn(), x, y, a);
                         cst += a.cost;
                         if (GRAD) { ggx += a.gx; ggy += a.gy; }
-                        hinge |= a.hr > 0.0;
+                        hit |= a.hr > 0.0;
                     }
                     if (!(met[i * N] > D)) {
                         EllT b;
                         ellipse_terms(GRAD, et + i * N, L.Ndyn() * N, x, y, b);
                         cst += b.cost;
                         if (GRAD) { ggx += b.gx; ggy += b.gy; }
-                        hinge |= b.hr > 0.0;
+                        hit |= b.hr > 0.0;
                     }
+                    if (hit && act[j]) { hm[(base >> 5) & 7] |= 1u << bit; hinge = true; }
                 }
             }
         }
@@ -634,8 +638,8 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
         }
 #pragma unroll 1
         for (int base = 0; base < L.Ndyn(); base += 32) {
-            const int it = base + lane;
-            const unsigned mk = __ballot_sync(FULL, it < L.Ndyn() && !(IM_E[it < L.Ndyn() ? it : 0] > dmax));
+            // only obstacles whose raw hinge was positive for some step (pass A) can differ from SP
+            const unsigned mk = __reduce_or_sync(FULL, hm[(base >> 5) & 7]);
             const int lim = L.Ndyn() - base < 32 ? L.Ndyn() - base : 32;
 #pragma unroll 1
             for (int bi = 0; bi < lim; ++bi) {

@@ -55,7 +55,7 @@ typedef struct mpcb_dims {
     int32_t Nother;  /* other robots                                            */
     int32_t Nstc;    /* static polygons (half-space form)                       */
     int32_t nedge;   /* edges per polygon = nstcobs/3 (reference: 4), 1..8      */
-    int32_t Ndyn;    /* dynamic-obstacle ellipses per time offset               */
+    int32_t Ndyn;    /* dynamic-obstacle ellipses per time offset (<= 256)      */
 } mpcb_dims;
 
 /* Robot / kinematic constants: config/mpc_fast.yaml:6-18 (configs.py:93-103). */
@@ -95,6 +95,7 @@ typedef struct mpcb_solver_cfg {
 #define MPCB_MAX_LBFGS 10
 #define MPCB_MAX_N     64
 #define MPCB_MAX_EDGE  8
+#define MPCB_MAX_NDYN  256
 
 /* Length of the parameter vector p for these dims (2778 at the yaml defaults). */
 int32_t mpcb_param_len(const mpcb_dims* dims);
