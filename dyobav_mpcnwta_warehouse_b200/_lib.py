@@ -19,7 +19,7 @@ ERRORS = {-1: "unsupported or inconsistent dimensions", -2: "required pointer is
 EXPORTS = ("mpcb_abi_version", "mpcb_last_error", "mpcb_param_len", "mpcb_num_decision", "mpcb_n1",
            "mpcb_n2", "mpcb_default_robot", "mpcb_default_solver_cfg", "mpcb_workspace_bytes",
            "mpcb_eval_f64", "mpcb_solve_f64", "mpcb_solve_one_host", "mpcb_pack_f64",
-           "mpcb_plant_step_f64", "mpcb_sincos_host")
+           "mpcb_plant_step_f64", "mpcb_sincos_host", "mpcb_cluster_f64")
 
 
 class CSim(ctypes.Structure):
@@ -62,6 +62,9 @@ def load():
     L.mpcb_pack_f64.argtypes = [pd, ctypes.POINTER(CSim), dp, vp]
     L.mpcb_plant_step_f64.restype = i32
     L.mpcb_plant_step_f64.argtypes = [pd, ctypes.POINTER(CSim), dp, vp]
+    L.mpcb_cluster_f64.restype = i32
+    L.mpcb_cluster_f64.argtypes = [pd, i32, i32, i32, ctypes.c_double, i32, ctypes.c_double, ctypes.c_double,
+                                   dp, dp, dp, dp, dp, vp]
     L.mpcb_sincos_host.restype = None
     L.mpcb_sincos_host.argtypes = [ctypes.c_double, ctypes.POINTER(ctypes.c_double),
                                    ctypes.POINTER(ctypes.c_double)]
@@ -82,3 +85,21 @@ def sincos_host(x: float):
     sn, cs = ctypes.c_double(), ctypes.c_double()
     load().mpcb_sincos_host(float(x), ctypes.byref(sn), ctypes.byref(cs))
     return sn.value, cs.value
+
+
+def cluster_hypotheses(dims, hyp, cur_pos, n_hyp=None, eps=1.0, min_samples=2, enlarge=2.0, human_size=0.2):
+    """Device-side SWTA hypotheses -> ``o_d`` [n, Ndyn, N+1, 6] (torch CUDA tensors in and out)."""
+    import torch
+    L = load()
+    n, N, K, _ = hyp.shape
+    H = cur_pos.shape[1]
+    if N != dims.N or not hyp.is_cuda or hyp.dtype != torch.float64 or not hyp.is_contiguous():
+        raise RuntimeError("hyp must be a contiguous float64 CUDA tensor [n, N, K, 2]")
+    od = torch.empty(n, dims.Ndyn, N + 1, 6, dtype=torch.float64, device=hyp.device)
+    scratch = torch.empty(n, N + 1, dtype=torch.int32, device=hyp.device)
+    cd = dims.to_c()
+    ptr = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    st = ctypes.c_void_p(torch.cuda.current_stream(hyp.device).cuda_stream)
+    check(L.mpcb_cluster_f64(ctypes.byref(cd), n, K, H, eps, min_samples, enlarge, human_size, ptr(hyp),
+                             ptr(n_hyp), ptr(cur_pos.contiguous()), ptr(od), ptr(scratch), st), "mpcb_cluster_f64")
+    return od

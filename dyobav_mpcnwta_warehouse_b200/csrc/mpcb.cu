@@ -750,4 +750,19 @@ int32_t mpcb_plant_step_f64(const mpcb_dims* d, const mpcb_sim* sim, const doubl
     return MPCB_OK;
 }
 
+int32_t mpcb_cluster_f64(const mpcb_dims* d, int32_t n, int32_t K, int32_t H, double eps, int32_t min_samples,
+                         double enlarge, double human_size, const double* hyp, const int32_t* n_hyp,
+                         const double* cur_pos, double* o_d, int32_t* scratch, void* stream)
+{
+    if (!d || !hyp || !cur_pos || !o_d || !scratch) return MPCB_E_NULL;
+    if (n < 1 || K < 1 || K > CL_MAXK || H < 0 || d->N < 1 || d->Ndyn < 1 || min_samples < 1) return MPCB_E_DIMS;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int total = n * (d->N + 1);
+    cluster_kernel<<<(total + 63) / 64, 64, 0, st>>>(n, d->N, K, H, d->Ndyn, eps, min_samples, enlarge,
+                                                     human_size, hyp, n_hyp, cur_pos, o_d, scratch);
+    cluster_fill_kernel<<<n, 128, 0, st>>>(n, d->N, d->Ndyn, scratch, o_d);
+    CUDA_TRY(cudaGetLastError());
+    return MPCB_OK;
+}
+
 }  // extern "C"

@@ -193,4 +193,100 @@ __global__ void plant_kernel(const SimArgs A, int N2, const double* __restrict__
     if (fabs(s[0] - A.goal[2 * e]) <= 0.5 && fabs(s[1] - A.goal[2 * e + 1]) <= 0.5 && fabs(v) < 0.4) A.done[e] = 1;
 }
 
+// K6 cluster_kernel: SWTA position hypotheses -> dynamic-obstacle slots.
+// One thread per (episode, time offset): DBSCAN(eps, min_samples) exactly as
+// sklearn.cluster.DBSCAN labels (utils_test.py:133-143; clusters numbered by their first core
+// point), then per cluster mean and enlarge*std (utils_test.py:145-151, numpy's row-order sums)
+// written as [mx, my, sx, sy, 0, 1] into o_d[cluster][t] (main_base.py:293-302).  Offsets with
+// fewer clusters leave [0,0,0,0,0,1] in the slots of used obstacles, unused obstacles stay 0.
+constexpr int CL_MAXK = 64;
+
+__global__ void cluster_kernel(int n, int N, int K, int H, int Ndyn, double eps, int min_samples,
+                               double enlarge, double human_size, const double* __restrict__ hyp,
+                               const int* __restrict__ n_hyp, const double* __restrict__ cur,
+                               double* __restrict__ od, int* __restrict__ ncl_out)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n * (N + 1)) return;
+    const int e = g / (N + 1), t = g - e * (N + 1);
+    double* out = od + (size_t)e * Ndyn * (N + 1) * 6;
+    if (t == 0) {                       // current positions with the pedestrians' size
+        for (int h = 0; h < H && h < Ndyn; ++h) {
+            double* o = out + ((size_t)h * (N + 1)) * 6;
+            o[0] = cur[((size_t)e * H + h) * 2]; o[1] = cur[((size_t)e * H + h) * 2 + 1];
+            o[2] = human_size; o[3] = human_size; o[4] = 0.0; o[5] = 1.0;
+        }
+        ncl_out[(size_t)e * (N + 1)] = H < Ndyn ? H : Ndyn;
+        return;
+    }
+    const double* X = hyp + ((size_t)(e * N + (t - 1)) * K) * 2;
+    const int k = n_hyp ? n_hyp[e * N + (t - 1)] : K;
+    signed char label[CL_MAXK];
+    unsigned long long nb[CL_MAXK];
+    unsigned char stack[CL_MAXK];
+    const double eps2 = eps * eps;
+    for (int i = 0; i < k; ++i) {
+        unsigned long long m = 0ull;
+        for (int j = 0; j < k; ++j) {
+            const double dx = X[2 * i] - X[2 * j], dy = X[2 * i + 1] - X[2 * j + 1];
+            if (dx * dx + dy * dy <= eps2) m |= 1ull << j;
+        }
+        nb[i] = m;
+        label[i] = -1;
+    }
+    int c = 0;
+    for (int i = 0; i < k; ++i) {
+        if (label[i] != -1 || __popcll(nb[i]) < min_samples) continue;
+        label[i] = (signed char)c;
+        int sp = 0;
+        stack[sp++] = (unsigned char)i;
+        while (sp) {
+            const int j = stack[--sp];
+            if (__popcll(nb[j]) >= min_samples) {
+                unsigned long long m = nb[j];
+                while (m) {
+                    const int v = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    if (label[v] == -1) { label[v] = (signed char)c; stack[sp++] = (unsigned char)v; }
+                }
+            }
+        }
+        ++c;
+    }
+    ncl_out[(size_t)e * (N + 1) + t] = c < Ndyn ? c : Ndyn;
+    for (int q = 0; q < c && q < Ndyn; ++q) {
+        double m0 = 0.0, m1 = 0.0;
+        int cnt = 0;
+        for (int i = 0; i < k; ++i)
+            if (label[i] == q) { m0 += X[2 * i]; m1 += X[2 * i + 1]; ++cnt; }
+        m0 /= cnt; m1 /= cnt;
+        double v0 = 0.0, v1 = 0.0;
+        for (int i = 0; i < k; ++i)
+            if (label[i] == q) {
+                v0 += (X[2 * i] - m0) * (X[2 * i] - m0);
+                v1 += (X[2 * i + 1] - m1) * (X[2 * i + 1] - m1);
+            }
+        double* o = out + ((size_t)q * (N + 1) + t) * 6;
+        o[0] = m0; o[1] = m1;
+        o[2] = sqrt(v0 / cnt) * enlarge + 0.0;
+        o[3] = sqrt(v1 / cnt) * enlarge + 0.0;
+        o[4] = 0.0; o[5] = 1.0;
+    }
+}
+
+// second pass: slots of used obstacles that no cluster filled become [0,0,0,0,0,1]
+__global__ void cluster_fill_kernel(int n, int N, int Ndyn, const int* __restrict__ ncl, double* __restrict__ od)
+{
+    const int e = blockIdx.x;
+    if (e >= n) return;
+    int nobs = 0;
+    for (int t = 0; t <= N; ++t) nobs = ncl[(size_t)e * (N + 1) + t] > nobs ? ncl[(size_t)e * (N + 1) + t] : nobs;
+    for (int i = threadIdx.x; i < Ndyn * (N + 1); i += blockDim.x) {
+        const int ob = i / (N + 1), t = i - ob * (N + 1);
+        double* o = od + ((size_t)e * Ndyn * (N + 1) + i) * 6;
+        if (ob >= nobs) { for (int k = 0; k < 6; ++k) o[k] = 0.0; }
+        else if (ob >= ncl[(size_t)e * (N + 1) + t]) { o[0] = o[1] = o[2] = o[3] = o[4] = 0.0; o[5] = 1.0; }
+    }
+}
+
 }  // namespace mpcb

@@ -170,3 +170,67 @@ def assemble_params(dims: Dims, cfg: MpcConfig, state, ref_states: np.ndarray,
     if len(params) != dims.np:
         raise ValueError(f"assembled {len(params)} parameters, layout needs {dims.np}")
     return params
+
+
+# ---------------------------------------------------------------------------------------------
+# SWTA hypotheses -> ellipses: MainBase.run_wta_prediction (main_base.py:175-208)
+# clusters the predictor's position hypotheses of every time offset with
+# DBSCAN(eps=1, min_samples=2) (utils_test.py:133-143) and fits (mean, 2*std) per cluster
+# (utils_test.py:145-151); run_one_step turns them into obstacle slots (main_base.py:293-302).
+def dbscan_labels(points: np.ndarray, eps: float = 1.0, min_samples: int = 2) -> np.ndarray:
+    """Labels as sklearn.cluster.DBSCAN assigns them (clusters numbered by their first core
+    point in index order, noise = -1), restated without sklearn."""
+    X = np.asarray(points, dtype=np.float64)
+    n = X.shape[0]
+    d2 = (X[:, None, 0] - X[None, :, 0]) * (X[:, None, 0] - X[None, :, 0]) + \
+         (X[:, None, 1] - X[None, :, 1]) * (X[:, None, 1] - X[None, :, 1])
+    nb = d2 <= eps * eps
+    core = nb.sum(1) >= min_samples
+    labels = -np.ones(n, dtype=np.int64)
+    c = 0
+    for i in range(n):
+        if labels[i] != -1 or not core[i]:
+            continue
+        labels[i] = c
+        stack = [i]
+        while stack:
+            j = stack.pop()
+            if core[j]:
+                for v in np.nonzero(nb[j])[0]:
+                    if labels[v] == -1:
+                        labels[v] = c
+                        stack.append(v)
+        c += 1
+    return labels
+
+
+def hypotheses_to_obstacles(dims: Dims, current_positions, hypotheses, human_size: float = 0.2,
+                            eps: float = 1.0, min_samples: int = 2, enlarge: float = 2.0):
+    """``o_d`` block [Ndyn, N+1, 6] from the current pedestrian positions and per-offset hypotheses
+    ``hypotheses[t]`` = array [K_t, 2] (t = 0..N-1 for offsets 1..N)."""
+    N = dims.N
+    mu_ll = [[tuple(p) for p in current_positions]]
+    sd_ll = [[(human_size, human_size) for _ in current_positions]]
+    for t in range(N):
+        H = np.asarray(hypotheses[t], dtype=np.float64)
+        lab = dbscan_labels(H, eps, min_samples)
+        mus, sds = [], []
+        for c in range(int(lab.max()) + 1 if lab.size else 0):
+            pts = H[lab == c]
+            n = pts.shape[0]
+            m0 = m1 = 0.0
+            for q in pts:                                   # np.mean(axis=0): rows added in order
+                m0 += q[0]; m1 += q[1]
+            m0 /= n; m1 /= n
+            v0 = v1 = 0.0
+            for q in pts:                                   # np.std: sqrt(sum((x-mean)^2)/n)
+                v0 += (q[0] - m0) * (q[0] - m0); v1 += (q[1] - m1) * (q[1] - m1)
+            mus.append((m0, m1))
+            sds.append((math.sqrt(v0 / n) * enlarge + 0.0, math.sqrt(v1 / n) * enlarge + 0.0))
+        mu_ll.append(mus)
+        sd_ll.append(sds)
+    obs = dyn_obstacles_from_predictions(dims, mu_ll, sd_ll)[: dims.Ndyn]
+    out = np.zeros((dims.Ndyn, N + 1, NDYNPAR))
+    for i, o in enumerate(obs):
+        out[i] = np.asarray(o, dtype=np.float64)
+    return out

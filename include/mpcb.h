@@ -211,6 +211,18 @@ int32_t mpcb_plant_step_f64(const mpcb_dims* dims, const mpcb_sim* sim, const do
 /* the portable sin/cos the kernels use, callable on the host (bit-identical) */
 void mpcb_sincos_host(double x, double* sn, double* cs);
 
+/* SWTA position hypotheses -> the o_d block, on the device.  Replaces
+ * MainBase.run_wta_prediction's clustering (main_base.py:196-207: DBSCAN(eps=1, min_samples=2)
+ * per time offset, utils_test.py:133-143, and the (mean, 2*std) fit, utils_test.py:145-151)
+ * and run_one_step's slot list (main_base.py:293-302).
+ *   hyp [n, N, K, 2] hypotheses of offsets 1..N (K <= 64), n_hyp [n, N] valid counts or NULL,
+ *   cur_pos [n, H, 2] current pedestrian positions, o_d [n, Ndyn, N+1, 6] output,
+ *   scratch [n, N+1] int32.  All DEVICE pointers. */
+int32_t mpcb_cluster_f64(const mpcb_dims* dims, int32_t n, int32_t K, int32_t H, double eps,
+                         int32_t min_samples, double enlarge, double human_size, const double* hyp,
+                         const int32_t* n_hyp, const double* cur_pos, double* o_d, int32_t* scratch,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

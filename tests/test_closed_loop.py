@@ -148,3 +148,30 @@ def test_device_closed_loop_equals_host_closed_loop_bitwise():
         assert bool(g.done[i].item()) == e.done
         if not e.done:
             assert int(g.idx_ref[i].item()) == e.idx_ref
+
+
+@pytest.mark.gpu
+def test_device_clustering_equals_host_restatement_bitwise():
+    """K6: SWTA hypotheses -> o_d on the device equals the host restatement of the
+    reference's DBSCAN + Gaussian fit (itself pinned to sklearn/numpy on the CPU) bit for bit."""
+    import torch
+    from dyobav_mpcnwta_warehouse_b200 import _lib, packing
+    d = Dims()
+    rng = np.random.default_rng(3)
+    n, K, H = 12, 40, 2
+    cur = rng.uniform(-5, 5, (n, H, 2))
+    hyp = np.zeros((n, d.N, K, 2))
+    for e in range(n):
+        vel = rng.uniform(-1, 1, (H, 3, 2))                      # 3 modes per pedestrian
+        for t in range(d.N):
+            pts = []
+            for h in range(H):
+                modes = rng.integers(0, 3, K // H)
+                pts.append(cur[e, h] + (t + 1) * 0.2 * vel[h, modes] + rng.normal(0, 0.25, (K // H, 2)))
+            hyp[e, t] = np.concatenate(pts)
+    od = _lib.cluster_hypotheses(d, torch.as_tensor(hyp, device="cuda"), torch.as_tensor(cur, device="cuda"))
+    torch.cuda.synchronize()
+    od = od.cpu().numpy()
+    for e in range(n):
+        ref = packing.hypotheses_to_obstacles(d, [tuple(c) for c in cur[e]], [hyp[e, t] for t in range(d.N)])
+        np.testing.assert_array_equal(od[e], ref)

@@ -110,3 +110,35 @@ def test_generator_is_deterministic_and_sane():
     u0 = instances.multistart_guesses(d, a, 8, 5)
     assert u0.shape == (512, 40) and (u0[0::8] == 0).all()
     assert np.allclose(u0[1::8, 0::2], 1.2) and (u0[1::8, 1::2] == 0).all()
+
+
+def test_dbscan_restatement_matches_sklearn():
+    """The reference clusters hypotheses with sklearn.cluster.DBSCAN(eps=1, min_samples=2)
+    (utils_test.py:133-143); the restated labelling must agree with it."""
+    from sklearn.cluster import DBSCAN
+    rng = np.random.default_rng(0)
+    for trial in range(40):
+        k = int(rng.integers(2, 41))
+        centres = rng.uniform(-4, 4, (int(rng.integers(1, 4)), 2))
+        X = centres[rng.integers(0, len(centres), k)] + rng.normal(0, rng.uniform(0.1, 0.8), (k, 2))
+        for ms in (2, 3):
+            ref = DBSCAN(eps=1.0, min_samples=ms).fit(X).labels_
+            got = packing.dbscan_labels(X, 1.0, ms)
+            assert np.array_equal(ref, got), (trial, ms)
+
+
+def test_hypotheses_to_obstacles_matches_numpy_fit():
+    rng = np.random.default_rng(1)
+    d = Dims()
+    cur = [(1.0, 2.0), (4.0, -1.0)]
+    hyp = [np.concatenate([np.array(cur[0]) + 0.2 * t + rng.normal(0, 0.2, (20, 2)),
+                           np.array(cur[1]) - 0.1 * t + rng.normal(0, 0.3, (20, 2))]) for t in range(d.N)]
+    od = packing.hypotheses_to_obstacles(d, cur, hyp)
+    assert od.shape == (15, 21, 6)
+    assert od[0, 0].tolist() == [1.0, 2.0, 0.2, 0.2, 0.0, 1.0] and od[1, 0].tolist() == [4.0, -1.0, 0.2, 0.2, 0.0, 1.0]
+    lab = packing.dbscan_labels(hyp[3])
+    for c in range(lab.max() + 1):
+        pts = hyp[3][lab == c]
+        np.testing.assert_array_equal(od[c, 4, :2], np.mean(pts, axis=0))          # bit-exact vs numpy
+        np.testing.assert_array_equal(od[c, 4, 2:4], np.std(pts, axis=0) * 2 + 0)
+    assert (od[:, :, 5][(od[:, :, :4] != 0).any(-1)] == 1).all()
