@@ -254,7 +254,10 @@ def main():
         "gpu_launches": 2 * args.steps,
         "clocks": clk.summary(),
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                     "frac": achieved / fp64_peak, "traffic": None,
+                     "frac": achieved / fp64_peak,
+                     # ncu dram__bytes_read+write of this kernel: 41 030 400 B for 16 384 solves
+                     # (profiles/r1_traffic_metrics.csv) = 2 504 B per solve, scaled to this launch
+                     "traffic": 2504.0 * B,
                      "note": "peak = nominal FP64 FMA pipe (148 SM x 64 FMA/clk x 1.965 GHz); "
                              "MEASURED_PEAKS.json holds no FP64 figure. achieved = SURVEY 8(d) work "
                              f"(W_psi={wps} flop, grad=3x, L-BFGS {W_LBFGS_FLOP:.0f}/iter) x evaluations "
