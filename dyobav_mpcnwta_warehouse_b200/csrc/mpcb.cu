@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(256) eval_kernel(const KParams P, const double
     const double cc = c ? c[b] : P.c_init;
     const int n2 = P.L.Ndyn > 0 ? P.L.Ndyn : 1;
     EvalOut<SPL> o;
-    eval_psi<SPL, false>(P, S, v, w, cc, ya, yw, true, o, lane, F2 ? F2 + (size_t)b * n2 : nullptr);
+    eval_psi<SPL, 0>(P, S, v, w, cc, ya, yw, true, o, lane, F2 ? F2 + (size_t)b * n2 : nullptr);
     if (lane == 0) {
         if (f) f[b] = o.f;
         if (psi) psi[b] = o.psi;
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(256) solve_kernel(const KParams P, const doubl
         if (b < P.B) {
             const int sc = b / P.starts;
             const double* S = SMEM ? scn + (size_t)(sc - sc0) * P.L.total : staged + (size_t)sc * P.L.total;
-            solve_worker<SPL, 0, false>(P, S, nullptr, nullptr, lb, b, lane, io);
+            solve_worker<SPL, 0, 0>(P, S, nullptr, nullptr, lb, b, lane, io);
         }
     }
 }
@@ -380,8 +380,8 @@ __global__ void __launch_bounds__(256) solve_kernel(const KParams P, const doubl
 // K1 (queue variant): every warp pulls its own next instance from the atomic queue, so a
 // slow instance never holds other warps at a CTA barrier; scenario blocks are read from the
 // staged copy in global memory (L1/L2-resident: with culling a solve touches a few KB of it).
-template <int SPL, bool FIXED>
-__global__ void __launch_bounds__(FIXED ? MPCB_QTHREADS_FIXED : MPCB_QTHREADS, MPCB_MIN_CTAS) solve_kernel_queue(const KParams P, const double* __restrict__ staged,
+template <int SPL, int FIXED>
+__global__ void __launch_bounds__(FIXED == 1 ? MPCB_QTHREADS_FIXED : MPCB_QTHREADS, MPCB_MIN_CTAS) solve_kernel_queue(const KParams P, const double* __restrict__ staged,
                                                           const SolveIO io, int* __restrict__ counter)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -413,7 +413,7 @@ constexpr size_t WS_HEADER = 256;   // bytes reserved for the work-queue counter
 struct Plan {
     KParams P;
     bool smem;
-    bool fixed;
+    int fixed;     // compiled-in dimension set (0: run-time dims)
     int spl;
     size_t smem_bytes;
 };
@@ -454,7 +454,7 @@ int make_plan(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solver_cfg* c,
     const size_t cap = 227 * 1024;
     const size_t blk = (size_t)P.L.total * 8, lbw = (size_t)P.lb_doubles * 8;
     pl.smem = false;
-    pl.fixed = false;
+    pl.fixed = 0;
     int best_wps = 0;
     for (int W = 8; W >= 1; W >>= 1) {
         int nsc;
@@ -475,12 +475,17 @@ int make_plan(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solver_cfg* c,
     if (best_wps < 8 || (mode != 1 && need_lbfgs)) {
         // queue variant (solve) / too few resident warps: read the staged blocks through L1/L2
         pl.smem = false;
-        constexpr Lay FXD = make_lay(MPCB_FIX_DIMS);
-        pl.fixed = need_lbfgs && env_int("MPCB_FIXED", 1) && d->N == FXD.N && d->Nother == FXD.Nother &&
-                   d->Nstc == FXD.Nstc && d->nedge == FXD.nedge && d->Ndyn == FXD.Ndyn &&
-                   c->lbfgs_mem == MPCB_FIX_MEM;
-        P.warps = env_int("MPCB_WARPS", pl.fixed ? MPCB_QTHREADS_FIXED / 32 : MPCB_QTHREADS / 32); P.nsc = 0;
-        if (P.warps < 1 || P.warps > (pl.fixed ? MPCB_QTHREADS_FIXED : MPCB_QTHREADS) / 32) P.warps = 8;
+        pl.fixed = 0;
+        if (need_lbfgs && env_int("MPCB_FIXED", 1) && c->lbfgs_mem == MPCB_FIX_MEM)
+            for (int fx = 1; fx <= MPCB_NUM_FIXED; ++fx) {
+                const Lay F = fixed_lay(fx);
+                if (d->N == F.N && d->Nother == F.Nother && d->Nstc == F.Nstc && d->nedge == F.nedge &&
+                    d->Ndyn == F.Ndyn)
+                    pl.fixed = fx;
+            }
+        const int maxw = (pl.fixed == 1 ? MPCB_QTHREADS_FIXED : MPCB_QTHREADS) / 32;
+        P.warps = env_int("MPCB_WARPS", maxw); P.nsc = 0;
+        if (P.warps < 1 || P.warps > maxw) P.warps = maxw < 8 ? maxw : 8;
         pl.smem_bytes = 16 + P.warps * lbw;
     }
     return MPCB_OK;
@@ -633,9 +638,11 @@ int32_t mpcb_solve_f64(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solve
     } while (0)
     if (pl.smem) { if (pl.spl == 1) LAUNCH_SOLVE(1, true); else LAUNCH_SOLVE(2, true); }
     else {
-        if (pl.fixed) LAUNCH_QUEUE(1, true);
-        else if (pl.spl == 1) LAUNCH_QUEUE(1, false);
-        else LAUNCH_QUEUE(2, false);
+        if (pl.fixed == 1) LAUNCH_QUEUE(1, 1);
+        else if (pl.fixed == 2) LAUNCH_QUEUE(1, 2);
+        else if (pl.fixed == 3) LAUNCH_QUEUE(2, 3);
+        else if (pl.spl == 1) LAUNCH_QUEUE(1, 0);
+        else LAUNCH_QUEUE(2, 0);
     }
 #undef LAUNCH_SOLVE
 #undef LAUNCH_QUEUE

@@ -118,17 +118,27 @@ __host__ __device__ constexpr Lay make_lay(int N, int Nother, int Nstc, int nedg
     return L;
 }
 
-// the dims of config/mpc_default.yaml / mpc_fast.yaml (lines 21-31): compiled in
-#define MPCB_FIX_DIMS 20, 10, 10, 4, 15
+// Dimension sets compiled into the solve kernel (FX > 0); FX = 0 is the run-time path.
+//   1: config/mpc_default.yaml / mpc_fast.yaml (lines 21-31)      - BASELINE configs[0,1,3]
+//   2: the same with 40 ellipses (2 pedestrians x 20 SWTA modes)  - BASELINE configs[2]
+//   3: dense crowd, N = 40, 160 ellipses                          - BASELINE configs[4]
 #define MPCB_FIX_MEM 10
+__host__ __device__ constexpr Lay fixed_lay(int fx)
+{
+    return fx == 1 ? make_lay(20, 10, 10, 4, 15)
+         : fx == 2 ? make_lay(20, 10, 10, 4, 40)
+         : fx == 3 ? make_lay(40, 10, 10, 4, 160)
+                   : make_lay(1, 0, 0, 1, 0);
+}
+constexpr int MPCB_NUM_FIXED = 3;
 
-template <bool FIXED>
+template <int FIXED>
 struct LayV {
     const Lay* r;
 #define MPCB_LAYF(name)                                                             \
     __device__ __forceinline__ int name() const                                     \
     {                                                                               \
-        if constexpr (FIXED) { constexpr int v = make_lay(MPCB_FIX_DIMS).name; return v; } \
+        if constexpr (FIXED != 0) { constexpr int v = fixed_lay(FIXED).name; return v; } \
         else return r->name;                                                        \
     }
     MPCB_LAYF(N) MPCB_LAYF(Nother) MPCB_LAYF(Nstc) MPCB_LAYF(nedge) MPCB_LAYF(Ndyn)
@@ -341,7 +351,7 @@ struct EvalOut {
 #ifndef MPCB_EVAL_ATTR
 #define MPCB_EVAL_ATTR __forceinline__
 #endif
-template <int SPL, bool FIXED>
+template <int SPL, int FIXED>
 __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restrict__ S,
                                          const double (&v)[SPL], const double (&w)[SPL], double c,
                                          const double (&ya)[SPL], const double (&yw)[SPL],

@@ -207,7 +207,7 @@ enum EvalFor { ST_INIT, ST_INIT_LIP, ST_LIP_HALF, ST_LIP_U0, ST_LIP_LOOP, ST_NOL
 //           meets at a barrier before each horizon evaluation, so the warps of an SM run the
 //           same code region at the same time (instruction-cache locality); warps that ran
 //           out of work keep the barrier matched until all are idle.
-template <int SPL, int MODE, bool FIXED>
+template <int SPL, int MODE, int FIXED>
 __device__ __forceinline__ void solve_worker(const KParams& P, const double* __restrict__ S0,
                                              const double* __restrict__ staged, int* __restrict__ counter,
                                              double* lb_mem, int b0, int lane, const SolveIO& io)
