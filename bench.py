@@ -154,6 +154,8 @@ def main():
     import torch.distributed as dist
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm")
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+        os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the one JSON line
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
