@@ -203,10 +203,6 @@ enum EvalFor { ST_INIT, ST_INIT_LIP, ST_LIP_HALF, ST_LIP_U0, ST_LIP_LOOP, ST_NOL
 // AlmOptimizer::solve + PANOCOptimizer::solve + PANOCEngine::{init,step}.
 //   MODE 0: solve the one instance b0 whose scenario block is S0, then return.
 //   MODE 1: queue worker — pull instances from `counter` until the batch is exhausted.
-//   MODE 2: queue worker whose evaluations are phase-aligned across the CTA: every warp
-//           meets at a barrier before each horizon evaluation, so the warps of an SM run the
-//           same code region at the same time (instruction-cache locality); warps that ran
-//           out of work keep the barrier matched until all are idle.
 template <int SPL, int MODE, int FIXED>
 __device__ __forceinline__ void solve_worker(const KParams& P, const double* __restrict__ S0,
                                              const double* __restrict__ staged, int* __restrict__ counter,
@@ -239,10 +235,7 @@ L_fetch:
         int nb = 0;
         if (lane == 0) nb = atomicAdd(counter, 1);
         b = __shfl_sync(FULL, nb, 0);
-        if (b >= P.B) {
-            if (MODE == 2) { while (__syncthreads_or(0)) {} }
-            return;
-        }
+        if (b >= P.B) return;
         S = staged + (size_t)(b / P.starts) * LV.total();
     }
     I.n_cost = 0; I.n_grad = 0;
@@ -285,7 +278,6 @@ L_outer_begin:   // ---- AlmOptimizer::step: project y on Y, then the inner prob
     want_grad = true; ceff = I.c; st = ST_INIT;
 
 L_eval:
-    if (MODE == 2) __syncthreads_or(1);
     eval_psi<SPL, FIXED>(P, S, pt0, pt1, ceff, I.ya, I.yw, want_grad, o, lane);
     if (want_grad) I.n_grad++; else I.n_cost++;
     switch (st) {
