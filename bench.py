@@ -255,7 +255,12 @@ def main():
             dist.destroy_process_group()
         return
 
-    fp64_peak = 148 * 64 * 2 * 1.965e9 / 1e12     # nominal: 64 FP64 FMA/clk/SM at max clock
+    fp64_nominal = 148 * 64 * 2 * 1.965e9 / 1e12  # 64 FP64 FMA/clk/SM at max clock
+    from dyobav_mpcnwta_warehouse_b200 import _lib
+    try:
+        fp64_peak, peak_src = _lib.fp64_peak_tflops(), "measured live: 8 independent DFMA chains/thread (mpcb_fp64_peak_tflops)"
+    except Exception as exc:                      # never fall back silently
+        raise RuntimeError(f"FP64 peak probe failed: {exc}")
     kernel_s = ms / 1e3 / args.steps
     achieved = flop_per_launch / kernel_s / 1e12
     line = {
@@ -273,8 +278,9 @@ def main():
                      # ncu dram__bytes_read+write of this kernel: 41 030 400 B for 16 384 solves
                      # (profiles/r1_traffic_metrics.csv) = 2 504 B per solve, scaled to this launch
                      "traffic": 2504.0 * B,
-                     "note": "peak = nominal FP64 FMA pipe (148 SM x 64 FMA/clk x 1.965 GHz); "
-                             "MEASURED_PEAKS.json holds no FP64 figure. achieved = SURVEY 8(d) work "
+                     "peak_source": peak_src, "peak_nominal": fp64_nominal,
+                     "note": "MEASURED_PEAKS.json holds no FP64 figure, so the FMA pipe is probed in this run "
+                             "(nominal 148 SM x 64 FMA/clk x 1.965 GHz = 37.2). achieved = SURVEY 8(d) work "
                              f"(W_psi={wps} flop, grad=3x, L-BFGS {W_LBFGS_FLOP:.0f}/iter) x evaluations "
                              "counted by the kernel / CUDA-event time",
                      "hbm": hbm_roofline((B * 8 * (dims.np / starts + 2 * dims.nu_total + 10)), kernel_s)},

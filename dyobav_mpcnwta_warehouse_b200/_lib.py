@@ -19,7 +19,7 @@ ERRORS = {-1: "unsupported or inconsistent dimensions", -2: "required pointer is
 EXPORTS = ("mpcb_abi_version", "mpcb_last_error", "mpcb_param_len", "mpcb_num_decision", "mpcb_n1",
            "mpcb_n2", "mpcb_default_robot", "mpcb_default_solver_cfg", "mpcb_workspace_bytes",
            "mpcb_eval_f64", "mpcb_solve_f64", "mpcb_solve_one_host", "mpcb_pack_f64",
-           "mpcb_plant_step_f64", "mpcb_sincos_host", "mpcb_cluster_f64")
+           "mpcb_plant_step_f64", "mpcb_sincos_host", "mpcb_cluster_f64", "mpcb_fp64_peak_tflops")
 
 
 class CSim(ctypes.Structure):
@@ -65,6 +65,8 @@ def load():
     L.mpcb_cluster_f64.restype = i32
     L.mpcb_cluster_f64.argtypes = [pd, i32, i32, i32, ctypes.c_double, i32, ctypes.c_double, ctypes.c_double,
                                    dp, dp, dp, dp, dp, vp]
+    L.mpcb_fp64_peak_tflops.restype = i32
+    L.mpcb_fp64_peak_tflops.argtypes = [ctypes.POINTER(ctypes.c_double)]
     L.mpcb_sincos_host.restype = None
     L.mpcb_sincos_host.argtypes = [ctypes.c_double, ctypes.POINTER(ctypes.c_double),
                                    ctypes.POINTER(ctypes.c_double)]
@@ -103,3 +105,10 @@ def cluster_hypotheses(dims, hyp, cur_pos, n_hyp=None, eps=1.0, min_samples=2, e
     check(L.mpcb_cluster_f64(ctypes.byref(cd), n, K, H, eps, min_samples, enlarge, human_size, ptr(hyp),
                              ptr(n_hyp), ptr(cur_pos.contiguous()), ptr(od), ptr(scratch), st), "mpcb_cluster_f64")
     return od
+
+
+def fp64_peak_tflops() -> float:
+    """Measured FP64 FMA throughput of the current CUDA device in TFLOP/s."""
+    v = ctypes.c_double()
+    check(load().mpcb_fp64_peak_tflops(ctypes.byref(v)), "mpcb_fp64_peak_tflops")
+    return v.value

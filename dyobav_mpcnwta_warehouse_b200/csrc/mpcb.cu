@@ -391,6 +391,20 @@ __global__ void __launch_bounds__(FIXED == 1 ? MPCB_QTHREADS_FIXED : MPCB_QTHREA
     solve_worker<SPL, 1, FIXED>(P, nullptr, staged, counter, lb, 0, lane, io);
 }
 
+// FP64 FMA throughput probe: the denominator of the roofline bench.py reports (the pool's
+// MEASURED_PEAKS.json has no FP64 figure).  8 independent DFMA chains per thread.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(int iters, double seed, double* sink)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+           a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678) *sink = a0;   // keep the chains alive
+}
+
 // ------------------------------------------------------------------ host side
 int build_layout(const mpcb_dims* d, Lay& L)
 {
@@ -769,6 +783,36 @@ int32_t mpcb_cluster_f64(const mpcb_dims* d, int32_t n, int32_t K, int32_t H, do
                                                      human_size, hyp, n_hyp, cur_pos, o_d, scratch);
     cluster_fill_kernel<<<n, 128, 0, st>>>(n, d->N, d->Ndyn, scratch, o_d);
     CUDA_TRY(cudaGetLastError());
+    return MPCB_OK;
+}
+
+/* Measured FP64 FMA throughput of the current device in TFLOP/s (2 flop per FMA). */
+int32_t mpcb_fp64_peak_tflops(double* tflops)
+{
+    if (!tflops) return MPCB_E_NULL;
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double* sink = nullptr;
+    CUDA_TRY(cudaMalloc(&sink, 8));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int iters = 1 << 15, grid = sms * 8;
+    fp64_peak_kernel<<<grid, 256>>>(1024, 1.0, sink);       // warm-up
+    float best = 1e30f;
+    for (int r = 0; r < 5; ++r) {
+        cudaEventRecord(e0);
+        fp64_peak_kernel<<<grid, 256>>>(iters, 1.0, sink);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        best = ms < best ? ms : best;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(sink);
+    CUDA_TRY(cudaGetLastError());
+    *tflops = 2.0 * 8.0 * iters * 256.0 * grid / (best * 1e-3) / 1e12;
     return MPCB_OK;
 }
 

@@ -223,6 +223,10 @@ int32_t mpcb_cluster_f64(const mpcb_dims* dims, int32_t n, int32_t K, int32_t H,
                          const int32_t* n_hyp, const double* cur_pos, double* o_d, int32_t* scratch,
                          void* stream);
 
+/* Measured FP64 FMA throughput of the current device (TFLOP/s, 2 flop per FMA): the roofline
+ * denominator bench.py reports for the solve kernel. */
+int32_t mpcb_fp64_peak_tflops(double* tflops);
+
 #ifdef __cplusplus
 }
 #endif
