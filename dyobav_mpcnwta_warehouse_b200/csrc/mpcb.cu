@@ -313,6 +313,8 @@ __global__ void __launch_bounds__(256) eval_kernel(const KParams P, const double
         }
     }
     const double cc = c ? c[b] : P.c_init;
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) { ya[j] = ya[j] / fmax(cc, 1.0); yw[j] = yw[j] / fmax(cc, 1.0); }
     const int n2 = P.L.Ndyn > 0 ? P.L.Ndyn : 1;
     EvalOut<SPL> o;
     eval_psi<SPL, 0>(P, S, v, w, cc, ya, yw, true, o, lane, F2 ? F2 + (size_t)b * n2 : nullptr);
@@ -461,7 +463,8 @@ int make_plan(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solver_cfg* c,
     P.B = (int)B;
     pl.spl = d->N <= 32 ? 1 : 2;
     const int M = c->lbfgs_mem + 1;
-    P.lb_doubles = need_lbfgs ? ((2 * M * 2 * d->N + 2 * M + 1) & ~1) : 0;
+    // per-warp scratch: L-BFGS rows + rho/alpha, then y and y+ (the Lagrange multipliers, 2N each)
+    P.lb_doubles = need_lbfgs ? (((2 * M * 2 * d->N + 2 * M + 1) & ~1) + 4 * d->N) : 0;
 
     // choose warps per CTA so that the scenario blocks + per-warp L-BFGS fit in
     // shared memory; fall back to reading the staged blocks from global (L1/L2)

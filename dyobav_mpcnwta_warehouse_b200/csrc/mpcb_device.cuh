@@ -185,22 +185,33 @@ __device__ MPCB_RED_ATTR double warp_sum(double v)
     for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(FULL, v, m);
     return v;
 }
+// One Kogge-Stone stage on a double: the shuffle's own "source lane in range" predicate
+// guards the add (2 SHFL + 1 predicated DADD per stage, no lane compare).
+#define MPCB_SCAN_STAGE(DIR, CLAMP, V, D)                                                     \
+    asm volatile("{\n\t"                                                                      \
+                 ".reg .pred p;\n\t"                                                          \
+                 ".reg .b32 lo, hi, tlo, thi;\n\t"                                            \
+                 ".reg .f64 t;\n\t"                                                           \
+                 "mov.b64 {lo, hi}, %0;\n\t"                                                  \
+                 "shfl.sync." DIR ".b32 tlo|p, lo, %1, " CLAMP ", 0xffffffff;\n\t"             \
+                 "shfl.sync." DIR ".b32 thi, hi, %1, " CLAMP ", 0xffffffff;\n\t"               \
+                 "mov.b64 t, {tlo, thi};\n\t"                                                 \
+                 "@p add.rn.f64 %0, %0, t;\n\t"                                               \
+                 "}"                                                                          \
+                 : "+d"(V)                                                                    \
+                 : "r"(D))
 __device__ MPCB_RED_ATTR double scan_incl(double v, int lane)
 {
+    (void)lane;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        double t = __shfl_up_sync(FULL, v, d);
-        if (lane >= d) v += t;
-    }
+    for (int d = 1; d < 32; d <<= 1) MPCB_SCAN_STAGE("up", "0", v, d);
     return v;
 }
 __device__ MPCB_RED_ATTR double rscan_incl(double v, int lane)
 {
+    (void)lane;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        double t = __shfl_down_sync(FULL, v, d);
-        if (lane + d < 32) v += t;
-    }
+    for (int d = 1; d < 32; d <<= 1) MPCB_SCAN_STAGE("down", "31", v, d);
     return v;
 }
 
@@ -347,7 +358,9 @@ struct EvalOut {
 
 // Evaluate psi(u; c, y) (and its gradient) for the instance owned by this warp.
 //   S: staged scenario block.  v/w: the point.  ya/yw: multipliers of the lane's
-//   two F1 entries (acc_k, wacc_k).  F2out (nullable, global): per-obstacle F2.
+//   two F1 entries (acc_k, wacc_k) ALREADY DIVIDED by max(c, 1) — the quotient only changes
+//   once per outer iteration, so the solver divides there and not in every evaluation.
+//   F2out (nullable, global): per-obstacle F2.
 #ifndef MPCB_EVAL_ATTR
 #define MPCB_EVAL_ATTR __forceinline__
 #endif
@@ -699,7 +712,6 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
     double dist2 = 0.0;
     {
         const double accp = q[8], waccp = q[9];
-        const double cdiv = fmax(c, 1.0);
         double vprev_carry = H[H_UM1V], wprev_carry = H[H_UM1W];
 #pragma unroll
         for (int j = 0; j < SPL; ++j) {
@@ -710,7 +722,7 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
                 wprev_carry = __shfl_sync(FULL, w[j], 31);
             }
             const double acc = (v[j] - vp) * P.inv_ts, wacc = (w[j] - wp) * P.inv_ts;
-            const double za = acc + ya[j] / cdiv, zw = wacc + yw[j] / cdiv;
+            const double za = acc + ya[j], zw = wacc + yw[j];
             const double ra = za > P.amax ? za - P.amax : (za < P.amin ? za - P.amin : 0.0);
             const double rwv = zw > P.wamax ? zw - P.wamax : (zw < -P.wamax ? zw + P.wamax : 0.0);
             if (act[j]) {
@@ -735,7 +747,9 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
     if (GRAD) {
         // adjoint: G = sum_{j>=k} g_j ; theta coupling via a second suffix sum
         double Gx[SPL], Gy[SPL], hh[SPL], Hex[SPL], Hin[SPL];
-        const double gthN_all = warp_sum(gthN);   // only the lane owning step N-1 is non-zero
+        // only the lane owning step N-1 holds a non-zero value: broadcasting it and adding +0.0
+        // gives the bits the butterfly sum over {x, 0, ..., 0} would (x + 0.0 in every lane)
+        const double gthN_all = __shfl_sync(FULL, gthN, (N - 1) & 31) + 0.0;
         suffix_incl<SPL>(gx, Gx, lane);
         suffix_incl<SPL>(gy, Gy, lane);
 #pragma unroll

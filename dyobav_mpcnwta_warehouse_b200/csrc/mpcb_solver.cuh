@@ -51,7 +51,8 @@ struct Inst {   // per-lane slice of the solver state of one instance
     double r0[SPL], r1[SPL];       // gamma_fpr
     double d0[SPL], d1[SPL];       // direction_lbfgs
     double s0[SPL], s1[SPL];       // gradient_step
-    double ya[SPL], yw[SPL];       // Lagrange multipliers of (acc_k, wacc_k)
+    double ya[SPL], yw[SPL];       // Lagrange multipliers of (acc_k, wacc_k) / max(c, 1); y itself
+                                   // lives in the warp's shared-memory scratch
     double c;                      // penalty
     double gamma, sigma, Lc, cost, norm_r, akkt_tol;
     int iter;
@@ -215,10 +216,12 @@ __device__ __forceinline__ void solve_worker(const KParams& P, const double* __r
     Inst<SPL> I;
     Lbfgs<SPL> B;
     B.bind(lb_mem, N, FIXED ? MPCB_FIX_MEM : P.mem);
+    // y and y+ (2N doubles each) follow the L-BFGS rows; lane k only touches entries k and N+k
+    double* const ysm = lb_mem + ((2 * B.M * 2 * N + 2 * B.M + 1) & ~1);
+    double* const ypsm = ysm + 2 * N;
     const double* __restrict__ S = S0;
     int b = b0;
 
-    double yp_a[SPL], yp_w[SPL];
     double pt0[SPL], pt1[SPL];          // the point of the pending evaluation
     double dy = 0.0, dy_plus = 0.0, f2n = 0.0, f2n_plus = 0.0, last_fpr = -1.0, fcost = 0.0;
     double cost_half = 0.0, rhs_ls = 0.0, tau = 1.0, ceff = 0.0;
@@ -245,16 +248,15 @@ L_fetch:
         I.gp0[j] = 0.0; I.gp1[j] = 0.0; I.g0[j] = 0.0; I.g1[j] = 0.0;
         I.h0[j] = 0.0; I.h1[j] = 0.0; I.r0[j] = 0.0; I.r1[j] = 0.0;
         I.d0[j] = 0.0; I.d1[j] = 0.0; I.s0[j] = 0.0; I.s1[j] = 0.0;
-        yp_a[j] = 0.0; yp_w[j] = 0.0; pt0[j] = 0.0; pt1[j] = 0.0;
+        pt0[j] = 0.0; pt1[j] = 0.0;
         if (act[j]) {
             if (io.u0) {
                 const double2 t = reinterpret_cast<const double2*>(io.u0 + (size_t)b * 2 * N)[k];
                 I.u0[j] = t.x; I.u1[j] = t.y;
             }
-            if (io.y0) {
-                I.ya[j] = io.y0[(size_t)b * 2 * N + k];
-                I.yw[j] = io.y0[(size_t)b * 2 * N + N + k];
-            }
+            ysm[k] = io.y0 ? io.y0[(size_t)b * 2 * N + k] : 0.0;
+            ysm[N + k] = io.y0 ? io.y0[(size_t)b * 2 * N + N + k] : 0.0;
+            ypsm[k] = 0.0; ypsm[N + k] = 0.0;
         }
     }
     dy = 0.0; dy_plus = 0.0; f2n = 0.0; f2n_plus = 0.0; last_fpr = -1.0; fcost = 0.0;
@@ -267,8 +269,16 @@ L_fetch:
 L_outer_begin:   // ---- AlmOptimizer::step: project y on Y, then the inner problem
     ++n_outer;
     MPCB_FORJ {
-        I.ya[j] = fmin(fmax(I.ya[j], -1e12), 1e12);
-        I.yw[j] = fmin(fmax(I.yw[j], -1e12), 1e12);
+        const int k = lane + 32 * j;
+        double ya_ = 0.0, yw_ = 0.0;
+        if (act[j]) {
+            ya_ = fmin(fmax(ysm[k], -1e12), 1e12);
+            yw_ = fmin(fmax(ysm[N + k], -1e12), 1e12);
+            ysm[k] = ya_; ysm[N + k] = yw_;
+        }
+        // psi uses y / max(c, 1): constant over the inner problem, divided once here
+        I.ya[j] = ya_ / fmax(I.c, 1.0);
+        I.yw[j] = yw_ / fmax(I.c, 1.0);
         I.gp0[j] = 0.0; I.gp1[j] = 0.0;   // set_akkt_tolerance zeroes the cached previous gradient
     }
     // PANOCEngine::init
@@ -459,12 +469,15 @@ H_ALM: {
         double vp = __shfl_up_sync(FULL, I.u0[j], 1), wp = __shfl_up_sync(FULL, I.u1[j], 1);
         if (lane == 0) { vp = vc; wp = wc; }
         if (SPL > 1) { vc = __shfl_sync(FULL, I.u0[j], 31); wc = __shfl_sync(FULL, I.u1[j], 31); }
+        const int k = lane + 32 * j;
+        const double ya_ = act[j] ? ysm[k] : 0.0, yw_ = act[j] ? ysm[N + k] : 0.0;
         const double acc = (I.u0[j] - vp) * P.inv_ts, wacc = (I.u1[j] - wp) * P.inv_ts;
-        const double za = acc + I.ya[j] / I.c, zw = wacc + I.yw[j] / I.c;
+        const double za = acc + ya_ / I.c, zw = wacc + yw_ / I.c;
         const double pa = fmin(fmax(za, P.amin), P.amax), pw = fmin(fmax(zw, -P.wamax), P.wamax);
-        yp_a[j] = act[j] ? I.ya[j] + I.c * (acc - pa) : 0.0;
-        yp_w[j] = act[j] ? I.yw[j] + I.c * (wacc - pw) : 0.0;
-        const double e0 = yp_a[j] - I.ya[j], e1 = yp_w[j] - I.yw[j];
+        const double ypa = act[j] ? ya_ + I.c * (acc - pa) : 0.0;
+        const double ypw = act[j] ? yw_ + I.c * (wacc - pw) : 0.0;
+        if (act[j]) { ypsm[k] = ypa; ypsm[N + k] = ypw; }
+        const double e0 = ypa - ya_, e1 = ypw - yw_;
         dsum = fma(e0, e0, fma(e1, e1, dsum));
     }
     dy_plus = sqrt(warp_sum(dsum));
@@ -480,7 +493,10 @@ H_ALM: {
     ++alm_iter;
     dy = dy_plus;
     f2n = f2n_plus;
-    MPCB_FORJ { I.ya[j] = yp_a[j]; I.yw[j] = yp_w[j]; }
+    MPCB_FORJ {
+        const int k = lane + 32 * j;
+        if (act[j]) { ysm[k] = ypsm[k]; ysm[N + k] = ypsm[N + k]; }
+    }
     if (outer < P.max_outer) { ++outer; goto L_outer_begin; }
     goto L_finish;
 }
@@ -492,8 +508,8 @@ L_finish:
         if (act[j]) {
             reinterpret_cast<double2*>(io.u_out + (size_t)b * 2 * N)[k] = make_double2(I.u0[j], I.u1[j]);
             if (io.y_out) {
-                io.y_out[(size_t)b * 2 * N + k] = yp_a[j];
-                io.y_out[(size_t)b * 2 * N + N + k] = yp_w[j];
+                io.y_out[(size_t)b * 2 * N + k] = ypsm[k];
+                io.y_out[(size_t)b * 2 * N + N + k] = ypsm[N + k];
             }
         }
     }

@@ -1,9 +1,12 @@
 #!/bin/bash
-# A/B timing of two builds of libmpcb in one GPU session: scripts/ab.sh <libA> <libB> [reps]
+# A/B timing of builds of libmpcb in one GPU session:
+#   scripts/ab.sh "<libA> <libB> ..." [reps] [profile_step args]
+# default workload: 2368 scenarios x 8 starts at the reference settings (18 944 solves, 10.7 waves of warps)
 D=$PWD/dyobav_mpcnwta_warehouse_b200/csrc
-REPS=${3:-3}
+REPS=${2:-2}
+ARGS=${3:-"2368 8"}
 for i in $(seq $REPS); do
-  for L in $1 $2; do
-    echo -n "$L: "; MPCB_LIB_PATH=$D/$L python scripts/profile_step.py 4736 8 100 3 | tail -1 | cut -c1-48
+  for L in $1; do
+    echo -n "$L: "; MPCB_LIB_PATH=$D/$L python scripts/profile_step.py $ARGS | tail -1 | cut -c1-60
   done
 done
