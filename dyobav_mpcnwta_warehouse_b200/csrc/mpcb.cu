@@ -388,7 +388,9 @@ __global__ void __launch_bounds__(FIXED == 1 ? MPCB_QTHREADS_FIXED : MPCB_QTHREA
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* lb_all = reinterpret_cast<double*>(smem_raw);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    asm volatile("" : "+r"(lane));   // keep the lane id in a register (S2R is slow to re-read)
     double* lb = lb_all + (size_t)warp * P.lb_doubles;
     solve_worker<SPL, 1, FIXED>(P, nullptr, staged, counter, lb, 0, lane, io);
 }

@@ -178,6 +178,21 @@ __host__ __device__ MPCB_HELPER_ATTR void sincos_cw(double x, double* sn, double
     *cs = ((q + 1) & 2) ? -c1 : c1;
 }
 
+// ---------------------------------------------------------------- scalar helpers
+// IEEE division / square root behind ONE out-of-line copy each: the solver's scalar bookkeeping
+// divides in a dozen places, and every inlined a/b is ~25 instructions of Newton iteration plus
+// a slow-path call.  The hot loop has to fit the SM's instruction cache (the kernel is bound by
+// instruction supply, not by any pipe), so these are calls.  Same bits as the inline forms.
+__device__ __noinline__ double ddiv(double a, double b) { return a / b; }
+__device__ __noinline__ double dsqrt(double a) { return sqrt(a); }
+// x / g for x >= 0: a zero numerator (no active bound: gradient step == half step) would send
+// the inline division down its ~60-instruction slow path; 0 / g is +0 for any finite g > 0.
+__device__ __forceinline__ double div_nonneg(double x, double g)
+{
+    if (x == 0.0 && g > 0.0 && g < INFINITY) return 0.0;
+    return ddiv(x, g);
+}
+
 // ---------------------------------------------------------------- warp helpers
 __device__ MPCB_RED_ATTR double warp_sum(double v)
 {
@@ -444,7 +459,7 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
             X[j] = H[H_S0X] + px[j];
             Y[j] = H[H_S0Y] + py[j];
             const double ax = X[j] - sg[k], ay = Y[j] - sg[N + k];
-            Df[j] = CULL ? __double2float_ru(fma(sqrt(fma(ax, ax, ay * ay)), 1.0 + 1e-9, 1e-9))
+            Df[j] = CULL ? __double2float_ru(fma(dsqrt(fma(ax, ax, ay * ay)), 1.0 + 1e-9, 1e-9))
                          : __int_as_float(0x7f800000);
             if (act[j]) {
                 dmax = fmaxf(dmax, Df[j]);

@@ -115,7 +115,7 @@ __device__ __forceinline__ void lbfgs_update(const KParams& P, Lbfgs<SPL>& B, co
     if (ss <= 2.2250738585072014e-308 || (P.sy_eps > 0.0 && ys <= P.sy_eps)) {
         ok = false;
     } else if (P.cb_eps > 0.0 && P.cb_alpha > 0.0) {
-        const double lhs = ys / ss;
+        const double lhs = ddiv(ys, ss);
         const double rhs = P.cb_eps * (P.cb_alpha == 1.0 ? I.norm_r : pow(I.norm_r, P.cb_alpha));
         ok = lhs > rhs && isfinite(lhs) && isfinite(rhs);
     } else {
@@ -134,8 +134,8 @@ __device__ __forceinline__ void lbfgs_update(const KParams& P, Lbfgs<SPL>& B, co
             yr[k] = yn0[j]; yr[B.N + k] = yn1[j];
         }
     }
-    if (lane == 0) B.rho[B.head] = 1.0 / ys;
-    B.gamma = ys / yy;
+    if (lane == 0) B.rho[B.head] = ddiv(1.0, ys);
+    B.gamma = ddiv(ys, yy);
     B.active = B.active + 1 < B.mem ? B.active + 1 : B.mem;
     __syncwarp();
 }
@@ -186,7 +186,7 @@ template <int SPL>
 __device__ __forceinline__ void compute_fpr(Inst<SPL>& I)
 {
     MPCB_FORJ { I.r0[j] = I.u0[j] - I.h0[j]; I.r1[j] = I.u1[j] - I.h1[j]; }
-    I.norm_r = sqrt(sumsq2<SPL>(I.r0, I.r1));
+    I.norm_r = dsqrt(sumsq2<SPL>(I.r0, I.r1));
 }
 
 struct SolveIO {
@@ -240,6 +240,9 @@ L_fetch:
         b = __shfl_sync(FULL, nb, 0);
         if (b >= P.B) return;
         S = staged + (size_t)(b / P.starts) * LV.total();
+        // opaque from here on: under register pressure the compiler would otherwise re-derive the
+        // pointer (an integer division) inside the evaluation instead of keeping it
+        asm volatile("" : "+l"(S));
     }
     I.n_cost = 0; I.n_grad = 0;
     MPCB_FORJ {
@@ -333,11 +336,11 @@ L_step_begin:   // ---- PANOCEngine::step
     if (I.norm_r < P.tol) {
         double a = 0.0;
         MPCB_FORJ {
-            const double t0 = I.r0[j] / I.gamma + I.g0[j] - I.gp0[j];
-            const double t1 = I.r1[j] / I.gamma + I.g1[j] - I.gp1[j];
+            const double t0 = ddiv(I.r0[j], I.gamma) + I.g0[j] - I.gp0[j];
+            const double t1 = ddiv(I.r1[j], I.gamma) + I.g1[j] - I.gp1[j];
             a = fma(t0, t0, fma(t1, t1, a));
         }
-        if (sqrt(warp_sum(a)) < I.akkt_tol) { flag = false; goto L_step_return; }
+        if (dsqrt(warp_sum(a)) < I.akkt_tol) { flag = false; goto L_step_return; }
     }
     // update_lipschitz_constant: cost at the half step first
     MPCB_FORJ { pt0[j] = I.h0[j]; pt1[j] = I.h1[j]; }
@@ -364,7 +367,7 @@ H_LIP_LOOP:
 
 L_lip_check: {
     const double ip = dotw<SPL>(I.g0, I.g1, I.r0, I.r1);
-    const double rhs = I.cost + 1e-6 * fabs(I.cost) - ip + (0.95 / (2.0 * I.gamma)) * (I.norm_r * I.norm_r);
+    const double rhs = I.cost + 1e-6 * fabs(I.cost) - ip + ddiv(0.95, 2.0 * I.gamma) * (I.norm_r * I.norm_r);
     if (cost_half > rhs && it_lip < 10 && I.Lc < 1e9) {
         B.reset();
         I.Lc *= 2.0;
@@ -374,7 +377,7 @@ L_lip_check: {
         st = ST_LIP_LOOP;
         goto L_eval;
     }
-    I.sigma = (1.0 - 0.95) / (4.0 * I.gamma);
+    I.sigma = ddiv(1.0 - 0.95, 4.0 * I.gamma);
     // lbfgs_direction
     lbfgs_update<SPL>(P, B, I, lane, act);
     if (I.iter > 0) {
@@ -394,7 +397,7 @@ L_lip_check: {
         dd = fma(e0, e0, fma(e1, e1, dd));
     }
     const double dist2 = warp_sum(dd);
-    const double fbe = I.cost - 0.5 * I.gamma * sumsq2<SPL>(I.g0, I.g1) + 0.5 * dist2 / I.gamma;
+    const double fbe = I.cost - 0.5 * I.gamma * sumsq2<SPL>(I.g0, I.g1) + div_nonneg(0.5 * dist2, I.gamma);
     rhs_ls = fbe - I.sigma * (I.norm_r * I.norm_r);
     tau = 1.0;
     ls = 0;
@@ -422,7 +425,7 @@ H_LS: {
         d2 = fma(e0, e0, fma(e1, e1, d2));
     }
     d2 = warp_sum(d2);
-    const double lhs = I.cost - 0.5 * I.gamma * sumsq2<SPL>(I.g0, I.g1) + 0.5 * d2 / I.gamma;
+    const double lhs = I.cost - 0.5 * I.gamma * sumsq2<SPL>(I.g0, I.g1) + div_nonneg(0.5 * d2, I.gamma);
     if (lhs > rhs_ls && ls < 10) {
         tau /= 2.0;
         ++ls;
