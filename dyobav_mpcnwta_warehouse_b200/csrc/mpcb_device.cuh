@@ -193,6 +193,11 @@ __device__ __forceinline__ double div_nonneg(double x, double g)
     return ddiv(x, g);
 }
 
+// max(0, r) and clamp to [0, 1] as plain selects (NaN -> 0, like fmax/fmin; a few instructions
+// instead of the library forms' NaN/signed-zero handling).  Same code in the laned oracle.
+__host__ __device__ __forceinline__ double pos_part(double r) { return r > 0.0 ? r : 0.0; }
+__host__ __device__ __forceinline__ double clamp01(double t) { return t > 0.0 ? (t < 1.0 ? t : 1.0) : 0.0; }
+
 // ---------------------------------------------------------------- warp helpers
 __device__ MPCB_RED_ATTR double warp_sum(double v)
 {
@@ -345,7 +350,7 @@ __device__ MPCB_HELPER_ATTR double polygon_ind(const bool GRAD, const double* __
 #pragma unroll 1
     for (int j = 0; j < nedge; ++j) {
         const double r = fma(e[3 * j + 2], y, fma(e[3 * j + 1], x, e[3 * j]));
-        I *= fmax(0.0, r);
+        I *= pos_part(r);
     }
     dIx = 0.0; dIy = 0.0;
     if (GRAD && I > 0.0) {
@@ -501,7 +506,7 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
                             const double ex = x - sg[i], ey = y - sg[N + i];
                             const double ddx = sg[2 * N + i], ddy = sg[3 * N + i];
                             const double th_ = fma(ex, ddx, ey * ddy) * sg[4 * N + i];
-                            const double ts_ = fmin(fmax(th_, 0.0), 1.0);
+                            const double ts_ = clamp01(th_);
                             const double vx = fma(ts_, ddx, -ex), vy = fma(ts_, ddy, -ey);
                             const double d2 = fma(vx, vx, vy * vy);
                             if (d2 < best) { best = d2; ib = i; }
@@ -514,7 +519,7 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
                 const double ex = x - sg[ib], ey = y - sg[N + ib];
                 const double ddx = sg[2 * N + ib], ddy = sg[3 * N + ib], inv = sg[4 * N + ib];
                 const double th_ = fma(ex, ddx, ey * ddy) * inv;
-                const double ts_ = fmin(fmax(th_, 0.0), 1.0);
+                const double ts_ = clamp01(th_);
                 const double vx = fma(ts_, ddx, -ex), vy = fma(ts_, ddy, -ey);
                 const double dt = (th_ > 0.0 && th_ < 1.0) ? 1.0 : ((th_ == 0.0 || th_ == 1.0) ? 0.5 : 0.0);
                 const double vd = fma(vx, ddx, vy * ddy) * dt * inv;

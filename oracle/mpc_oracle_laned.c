@@ -49,6 +49,10 @@ typedef struct {
 enum { E_CX = 0, E_CY, E_CA, E_SA, E_I1I, E_I2I, E_I1R, E_I2R, E_WAL, EF };
 
 /* ---- sin/cos: Cody-Waite by pi/2 + fdlibm kernel polynomials (Horner, fma) ---- */
+/* max(0, r) and clamp to [0, 1] as the kernel writes them (plain selects; NaN -> 0) */
+static inline double pos_part(double r) { return r > 0.0 ? r : 0.0; }
+static inline double clamp01(double t) { return t > 0.0 ? (t < 1.0 ? t : 1.0) : 0.0; }
+
 static void sincos_cw(double x, double* sn, double* cs)
 {
     const double fn = rint(x * 6.36619772367581382433e-01);
@@ -276,7 +280,7 @@ static double polygon_ind(int GRAD, const double* e, int nedge, double x, double
     double I = 1.0;
     for (int j = 0; j < nedge; ++j) {
         const double r = fma(e[3 * j + 2], y, fma(e[3 * j + 1], x, e[3 * j]));
-        I *= fmax(0.0, r);
+        I *= pos_part(r);
     }
     *dIx = 0.0; *dIy = 0.0;
     if (GRAD && I > 0.0) {
@@ -351,7 +355,7 @@ static void eval_psi(const scen_t* S, lanes_t v, lanes_t w, double c, lanes_t ya
                     const double ex = x - S->sgx[i], ey = y - S->sgy[i];
                     const double ddx = S->sdx[i], ddy = S->sdy[i];
                     const double th_ = fma(ex, ddx, ey * ddy) * S->sinv[i];
-                    const double ts_ = fmin(fmax(th_, 0.0), 1.0);
+                    const double ts_ = clamp01(th_);
                     const double vx = fma(ts_, ddx, -ex), vy = fma(ts_, ddy, -ey);
                     const double d2 = fma(vx, vx, vy * vy);
                     if (d2 < best) { best = d2; ib = i; }
@@ -361,7 +365,7 @@ static void eval_psi(const scen_t* S, lanes_t v, lanes_t w, double c, lanes_t ya
                     const double ex = x - S->sgx[ib], ey = y - S->sgy[ib];
                     const double ddx = S->sdx[ib], ddy = S->sdy[ib], inv = S->sinv[ib];
                     const double th_ = fma(ex, ddx, ey * ddy) * inv;
-                    const double ts_ = fmin(fmax(th_, 0.0), 1.0);
+                    const double ts_ = clamp01(th_);
                     const double vx = fma(ts_, ddx, -ex), vy = fma(ts_, ddy, -ey);
                     const double dt = (th_ > 0.0 && th_ < 1.0) ? 1.0 : ((th_ == 0.0 || th_ == 1.0) ? 0.5 : 0.0);
                     const double vd = fma(vx, ddx, vy * ddy) * dt * inv;
