@@ -27,7 +27,8 @@
 #define MPCB_QTHREADS 256
 #endif
 #ifndef MPCB_QTHREADS_FIXED
-#define MPCB_QTHREADS_FIXED 384   // 12 warps x 168 registers: best measured for the default dims
+#define MPCB_QTHREADS_FIXED 512   // 16 warps x 128 registers (solver state parked in shared memory during the
+                                  // evaluation, per-CTA queues keep L1 on 2-3 scenario blocks): best measured
 #endif
 #ifndef MPCB_MIN_CTAS
 #define MPCB_MIN_CTAS 1
@@ -426,7 +427,7 @@ int env_int(const char* name, int dflt)
     return v && *v ? atoi(v) : dflt;
 }
 
-constexpr size_t WS_HEADER = 256;   // bytes reserved for the work-queue counter
+constexpr size_t WS_HEADER = 4096;  // bytes reserved for the work-queue counters (one per CTA)
 
 struct Plan {
     KParams P;
@@ -465,8 +466,8 @@ int make_plan(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solver_cfg* c,
     P.B = (int)B;
     pl.spl = d->N <= 32 ? 1 : 2;
     const int M = c->lbfgs_mem + 1;
-    // per-warp scratch: L-BFGS rows + rho/alpha, then y and y+ (the Lagrange multipliers, 2N each)
-    P.lb_doubles = need_lbfgs ? (((2 * M * 2 * d->N + 2 * M + 1) & ~1) + 4 * d->N) : 0;
+    // per-warp scratch: L-BFGS rows + rho/alpha, then y, y+ and the parked solver state
+    P.lb_doubles = need_lbfgs ? (((2 * M * 2 * d->N + 2 * M + 1) & ~1) + scratch_doubles(d->N)) : 0;
 
     // choose warps per CTA so that the scenario blocks + per-warp L-BFGS fit in
     // shared memory; fall back to reading the staged blocks from global (L1/L2)
@@ -505,6 +506,7 @@ int make_plan(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solver_cfg* c,
         const int maxw = (pl.fixed == 1 ? MPCB_QTHREADS_FIXED : MPCB_QTHREADS) / 32;
         P.warps = env_int("MPCB_WARPS", maxw); P.nsc = 0;
         if (P.warps < 1 || P.warps > maxw) P.warps = maxw < 8 ? maxw : 8;
+        while (P.warps > 1 && 16 + P.warps * lbw > cap) --P.warps;   // large N: fewer warps per CTA
         pl.smem_bytes = 16 + P.warps * lbw;
     }
     return MPCB_OK;
@@ -653,6 +655,7 @@ int32_t mpcb_solve_f64(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solve
         if (env_int("MPCB_CTAS_PER_SM", 0) > 0) per_sm = env_int("MPCB_CTAS_PER_SM", 0);           \
         int grid = sms * per_sm;                                                                   \
         if (grid > ngroups) grid = ngroups;                                                        \
+        if (grid > (int)(WS_HEADER / sizeof(int))) grid = (int)(WS_HEADER / sizeof(int));          \
         solve_kernel_queue<SPL, MD><<<grid, threads, pl.smem_bytes, st>>>(pl.P, staged, io, counter); \
     } while (0)
     if (pl.smem) { if (pl.spl == 1) LAUNCH_SOLVE(1, true); else LAUNCH_SOLVE(2, true); }

@@ -53,11 +53,25 @@ struct Inst {   // per-lane slice of the solver state of one instance
     double s0[SPL], s1[SPL];       // gradient_step
     double ya[SPL], yw[SPL];       // Lagrange multipliers of (acc_k, wacc_k) / max(c, 1); y itself
                                    // lives in the warp's shared-memory scratch
-    double c;                      // penalty
-    double gamma, sigma, Lc, cost, norm_r, akkt_tol;
+    double gamma, sigma, Lc, cost, norm_r;
     int iter;
-    int n_cost, n_grad;
 };
+
+// Outer-loop (ALM) state of one instance: touched once per outer iteration, so it lives in the
+// warp's shared-memory scratch for good (every lane writes the same value: a benign broadcast).
+struct ColdState {
+    double c;                      // penalty
+    double akkt_tol;
+    double dy, dy_plus, f2n, f2n_plus, last_fpr, fcost;
+    int alm_iter, n_outer, inner_total, outer, inner, status, n_cost, n_grad;
+    int failed, qscan, pad[2];     // sizeof == 112: keeps the scratch a whole number of double2
+};
+// doubles of per-warp scratch after the L-BFGS rows: y, y+ (2N each), the parked solver vectors
+// (9 x (v, w) per horizon step), the parked PANOC scalars and the cold state
+__host__ __device__ constexpr int scratch_doubles(int N)
+{
+    return 4 * N + 9 * 2 * N + 16 + (int)(sizeof(ColdState) / 8);
+}
 
 #define MPCB_FORJ _Pragma("unroll") for (int j = 0; j < SPL; ++j)
 
@@ -219,32 +233,55 @@ __device__ __forceinline__ void solve_worker(const KParams& P, const double* __r
     // y and y+ (2N doubles each) follow the L-BFGS rows; lane k only touches entries k and N+k
     double* const ysm = lb_mem + ((2 * B.M * 2 * N + 2 * B.M + 1) & ~1);
     double* const ypsm = ysm + 2 * N;
+    // While the horizon evaluation runs (75 % of the time, ~100 live registers of its own) the
+    // solver's vectors and most of its scalars are parked in shared memory: no spills inside the
+    // evaluation's loops, and room for more resident warps per SM.
+    double2* const vpark = reinterpret_cast<double2*>(ypsm + 2 * N);
+    double* const spark = reinterpret_cast<double*>(vpark + 9 * N);
+    ColdState* const CS = reinterpret_cast<ColdState*>(spark + 16);
+#define MPCB_PARK_V(idx, a0, a1) MPCB_FORJ { if (act[j]) vpark[(idx) * N + lane + 32 * j] = make_double2(a0[j], a1[j]); }
+#define MPCB_FILL_V(idx, a0, a1) MPCB_FORJ { if (act[j]) { const double2 t_ = vpark[(idx) * N + lane + 32 * j]; a0[j] = t_.x; a1[j] = t_.y; } }
     const double* __restrict__ S = S0;
     int b = b0;
 
     double pt0[SPL], pt1[SPL];          // the point of the pending evaluation
-    double dy = 0.0, dy_plus = 0.0, f2n = 0.0, f2n_plus = 0.0, last_fpr = -1.0, fcost = 0.0;
     double cost_half = 0.0, rhs_ls = 0.0, tau = 1.0, ceff = 0.0;
-    int alm_iter = 0, n_outer = 0, inner_total = 0, outer = 1;
-    int num_iter = 0, it_lip = 0, ls = 0, inner = MPCB_CONVERGED;
-    int status = MPCB_CONVERGED;
+    int num_iter = 0, it_lip = 0, ls = 0;
     int st = ST_INIT;
-    bool cont = true, flag = true, want_grad = true, failed = false;
+    bool cont = true, flag = true, want_grad = true;
     const double EPS = 2.220446049250313e-16;
     EvalOut<SPL> o;
+    CS->qscan = 0;
 
 L_fetch:
     if (MODE != 0) {
-        int nb = 0;
-        if (lane == 0) nb = atomicAdd(counter, 1);
-        b = __shfl_sync(FULL, nb, 0);
-        if (b >= P.B) return;
-        S = staged + (size_t)(b / P.starts) * LV.total();
+        // One queue per CTA: queue q owns scenarios q, q + nq, q + 2 nq, ... with all multi-start
+        // guesses of a scenario adjacent, so the warps of a CTA work on two or three scenario
+        // blocks at a time (L1 locality) instead of one each.  A warp whose own queue has run dry
+        // steals single instances from the following queues.
+        const int nq = gridDim.x;
+        int sc = -1;
+        for (int qs = CS->qscan; qs < nq; ++qs) {
+            int q = (int)blockIdx.x + qs;
+            if (q >= nq) q -= nq;
+            const int nsc_q = q < P.n_p ? (P.n_p - q + nq - 1) / nq : 0;
+            int t = 0;
+            if (lane == 0) t = atomicAdd(counter + q, 1);
+            t = __shfl_sync(FULL, t, 0);
+            if (t < nsc_q * P.starts) {
+                sc = q + (t / P.starts) * nq;
+                b = sc * P.starts + t % P.starts;
+                CS->qscan = qs;
+                break;
+            }
+        }
+        if (sc < 0) return;
+        S = staged + (size_t)sc * LV.total();
         // opaque from here on: under register pressure the compiler would otherwise re-derive the
         // pointer (an integer division) inside the evaluation instead of keeping it
         asm volatile("" : "+l"(S));
     }
-    I.n_cost = 0; I.n_grad = 0;
+    CS->n_cost = 0; CS->n_grad = 0;
     MPCB_FORJ {
         const int k = lane + 32 * j;
         I.u0[j] = 0.0; I.u1[j] = 0.0; I.ya[j] = 0.0; I.yw[j] = 0.0;
@@ -262,15 +299,15 @@ L_fetch:
             ypsm[k] = 0.0; ypsm[N + k] = 0.0;
         }
     }
-    dy = 0.0; dy_plus = 0.0; f2n = 0.0; f2n_plus = 0.0; last_fpr = -1.0; fcost = 0.0;
-    alm_iter = 0; n_outer = 0; inner_total = 0; outer = 1;
-    status = MPCB_CONVERGED; failed = false;
-    I.c = io.c0 ? io.c0[b] : P.c_init;
-    I.akkt_tol = P.tol0;
+    CS->dy = 0.0; CS->dy_plus = 0.0; CS->f2n = 0.0; CS->f2n_plus = 0.0; CS->last_fpr = -1.0; CS->fcost = 0.0;
+    CS->alm_iter = 0; CS->n_outer = 0; CS->inner_total = 0; CS->outer = 1;
+    CS->status = MPCB_CONVERGED; CS->failed = 0; CS->inner = MPCB_CONVERGED;
+    CS->c = io.c0 ? io.c0[b] : P.c_init;
+    CS->akkt_tol = P.tol0;
     I.gamma = 0.0; I.sigma = 0.0; I.Lc = 0.0; I.cost = 0.0; I.norm_r = 0.0; I.iter = 0;
 
 L_outer_begin:   // ---- AlmOptimizer::step: project y on Y, then the inner problem
-    ++n_outer;
+    CS->n_outer = CS->n_outer + 1;
     MPCB_FORJ {
         const int k = lane + 32 * j;
         double ya_ = 0.0, yw_ = 0.0;
@@ -280,19 +317,46 @@ L_outer_begin:   // ---- AlmOptimizer::step: project y on Y, then the inner prob
             ysm[k] = ya_; ysm[N + k] = yw_;
         }
         // psi uses y / max(c, 1): constant over the inner problem, divided once here
-        I.ya[j] = ya_ / fmax(I.c, 1.0);
-        I.yw[j] = yw_ / fmax(I.c, 1.0);
+        I.ya[j] = ya_ / fmax(CS->c, 1.0);
+        I.yw[j] = yw_ / fmax(CS->c, 1.0);
         I.gp0[j] = 0.0; I.gp1[j] = 0.0;   // set_akkt_tolerance zeroes the cached previous gradient
     }
     // PANOCEngine::init
     B.reset();
     I.iter = 0; num_iter = 0; cont = true;
     MPCB_FORJ { pt0[j] = I.u0[j]; pt1[j] = I.u1[j]; }
-    want_grad = true; ceff = I.c; st = ST_INIT;
+    want_grad = true; ceff = CS->c; st = ST_INIT;
 
 L_eval:
+    // park
+    MPCB_PARK_V(0, I.u0, I.u1); MPCB_PARK_V(1, I.g0, I.g1); MPCB_PARK_V(2, I.gp0, I.gp1);
+    MPCB_PARK_V(3, I.h0, I.h1); MPCB_PARK_V(4, I.r0, I.r1); MPCB_PARK_V(5, I.d0, I.d1);
+    MPCB_PARK_V(6, I.s0, I.s1); MPCB_PARK_V(7, B.os0, B.os1); MPCB_PARK_V(8, B.og0, B.og1);
+    spark[0] = I.sigma; spark[1] = I.Lc; spark[2] = I.norm_r; spark[3] = cost_half;
+    spark[4] = rhs_ls; spark[5] = tau; spark[6] = B.gamma;
+    reinterpret_cast<int*>(spark + 8)[0] = num_iter;
+    reinterpret_cast<int*>(spark + 8)[1] = it_lip;
+    reinterpret_cast<int*>(spark + 8)[2] = ls;
+    reinterpret_cast<int*>(spark + 8)[3] = B.head;
+    reinterpret_cast<int*>(spark + 8)[4] = B.active;
     eval_psi<SPL, FIXED>(P, S, pt0, pt1, ceff, I.ya, I.yw, want_grad, o, lane);
-    if (want_grad) I.n_grad++; else I.n_cost++;
+    // un-park (inactive lanes hold zeros in every vector)
+    MPCB_FORJ {
+        I.u0[j] = 0.0; I.u1[j] = 0.0; I.g0[j] = 0.0; I.g1[j] = 0.0; I.gp0[j] = 0.0; I.gp1[j] = 0.0;
+        I.h0[j] = 0.0; I.h1[j] = 0.0; I.r0[j] = 0.0; I.r1[j] = 0.0; I.d0[j] = 0.0; I.d1[j] = 0.0;
+        I.s0[j] = 0.0; I.s1[j] = 0.0; B.os0[j] = 0.0; B.os1[j] = 0.0; B.og0[j] = 0.0; B.og1[j] = 0.0;
+    }
+    MPCB_FILL_V(0, I.u0, I.u1); MPCB_FILL_V(1, I.g0, I.g1); MPCB_FILL_V(2, I.gp0, I.gp1);
+    MPCB_FILL_V(3, I.h0, I.h1); MPCB_FILL_V(4, I.r0, I.r1); MPCB_FILL_V(5, I.d0, I.d1);
+    MPCB_FILL_V(6, I.s0, I.s1); MPCB_FILL_V(7, B.os0, B.os1); MPCB_FILL_V(8, B.og0, B.og1);
+    I.sigma = spark[0]; I.Lc = spark[1]; I.norm_r = spark[2]; cost_half = spark[3];
+    rhs_ls = spark[4]; tau = spark[5]; B.gamma = spark[6];
+    num_iter = reinterpret_cast<int*>(spark + 8)[0];
+    it_lip = reinterpret_cast<int*>(spark + 8)[1];
+    ls = reinterpret_cast<int*>(spark + 8)[2];
+    B.head = reinterpret_cast<int*>(spark + 8)[3];
+    B.active = reinterpret_cast<int*>(spark + 8)[4];
+    if (want_grad) CS->n_grad = CS->n_grad + 1; else CS->n_cost = CS->n_cost + 1;
     switch (st) {
         case ST_INIT: goto H_INIT;
         case ST_INIT_LIP: goto H_INIT_LIP;
@@ -340,7 +404,7 @@ L_step_begin:   // ---- PANOCEngine::step
             const double t1 = ddiv(I.r1[j], I.gamma) + I.g1[j] - I.gp1[j];
             a = fma(t0, t0, fma(t1, t1, a));
         }
-        if (dsqrt(warp_sum(a)) < I.akkt_tol) { flag = false; goto L_step_return; }
+        if (dsqrt(warp_sum(a)) < CS->akkt_tol) { flag = false; goto L_step_return; }
     }
     // update_lipschitz_constant: cost at the half step first
     MPCB_FORJ { pt0[j] = I.h0[j]; pt1[j] = I.h1[j]; }
@@ -451,20 +515,21 @@ L_step_return:   // PANOCOptimizer::solve: flag = step(); while (flag && cont) {
     {
         bool fin = true;
         MPCB_FORJ fin = fin && isfinite(I.u0[j]) && isfinite(I.u1[j]);
-        if (!__all_sync(FULL, fin)) { status = MPCB_NOT_FINITE_COMPUTATION; failed = true; goto L_finish; }
+        if (!__all_sync(FULL, fin)) { CS->status = MPCB_NOT_FINITE_COMPUTATION; CS->failed = 1; goto L_finish; }
     }
     MPCB_FORJ { I.u0[j] = I.h0[j]; I.u1[j] = I.h1[j]; }   // return u_bar (always feasible)
-    inner = cont ? MPCB_CONVERGED : MPCB_NOT_CONVERGED_ITERATIONS;
-    last_fpr = I.norm_r;
-    inner_total += num_iter;
+    CS->inner = cont ? MPCB_CONVERGED : MPCB_NOT_CONVERGED_ITERATIONS;
+    CS->last_fpr = I.norm_r;
+    CS->inner_total = CS->inner_total + num_iter;
     // F1(u), F2(u), f(u) at the inner solution: one horizon evaluation with c = 0
     MPCB_FORJ { pt0[j] = I.u0[j]; pt1[j] = I.u1[j]; }
     want_grad = false; ceff = 0.0; st = ST_ALM;
     goto L_eval;
 
 H_ALM: {
-    fcost = o.f;
-    f2n_plus = sqrt(o.f2sq);
+    const double cpen = CS->c;
+    const double fcost = o.f;
+    const double f2n_plus = sqrt(o.f2sq);
     // update_lagrange_multipliers: y+ = y + c (F1 - Proj_C(F1 + y/c))
     double dsum = 0.0;
     double vc = S[LV.o_hdr() + H_UM1V], wc = S[LV.o_hdr() + H_UM1W];
@@ -475,37 +540,40 @@ H_ALM: {
         const int k = lane + 32 * j;
         const double ya_ = act[j] ? ysm[k] : 0.0, yw_ = act[j] ? ysm[N + k] : 0.0;
         const double acc = (I.u0[j] - vp) * P.inv_ts, wacc = (I.u1[j] - wp) * P.inv_ts;
-        const double za = acc + ya_ / I.c, zw = wacc + yw_ / I.c;
+        const double za = acc + ya_ / cpen, zw = wacc + yw_ / cpen;
         const double pa = fmin(fmax(za, P.amin), P.amax), pw = fmin(fmax(zw, -P.wamax), P.wamax);
-        const double ypa = act[j] ? ya_ + I.c * (acc - pa) : 0.0;
-        const double ypw = act[j] ? yw_ + I.c * (wacc - pw) : 0.0;
+        const double ypa = act[j] ? ya_ + cpen * (acc - pa) : 0.0;
+        const double ypw = act[j] ? yw_ + cpen * (wacc - pw) : 0.0;
         if (act[j]) { ypsm[k] = ypa; ypsm[N + k] = ypw; }
         const double e0 = ypa - ya_, e1 = ypw - yw_;
         dsum = fma(e0, e0, fma(e1, e1, dsum));
     }
-    dy_plus = sqrt(warp_sum(dsum));
+    const double dy_plus = sqrt(warp_sum(dsum));
+    CS->fcost = fcost; CS->f2n_plus = f2n_plus; CS->dy_plus = dy_plus;
     // is_exit_criterion_satisfied
-    const bool c1 = alm_iter > 0 && dy_plus <= I.c * P.delta + EPS;
+    const int alm_iter = CS->alm_iter;
+    const double akkt_tol = CS->akkt_tol;
+    const bool c1 = alm_iter > 0 && dy_plus <= cpen * P.delta + EPS;
     const bool c2 = f2n_plus <= P.delta + EPS;
-    const bool c3 = I.akkt_tol <= P.tol + EPS;
-    if (c1 && c2 && c3) { status = inner; goto L_finish; }
+    const bool c3 = akkt_tol <= P.tol + EPS;
+    if (c1 && c2 && c3) { CS->status = CS->inner; goto L_finish; }
     // is_penalty_stall_criterion
-    const bool stall = alm_iter == 0 || (dy_plus <= P.theta * dy + EPS && f2n_plus <= P.theta * f2n + EPS);
-    if (!stall) I.c *= P.rho;
-    I.akkt_tol = fmax(I.akkt_tol * P.beta, P.tol);
-    ++alm_iter;
-    dy = dy_plus;
-    f2n = f2n_plus;
+    const bool stall = alm_iter == 0 || (dy_plus <= P.theta * CS->dy + EPS && f2n_plus <= P.theta * CS->f2n + EPS);
+    if (!stall) CS->c = cpen * P.rho;
+    CS->akkt_tol = fmax(akkt_tol * P.beta, P.tol);
+    CS->alm_iter = alm_iter + 1;
+    CS->dy = dy_plus;
+    CS->f2n = f2n_plus;
     MPCB_FORJ {
         const int k = lane + 32 * j;
         if (act[j]) { ysm[k] = ypsm[k]; ysm[N + k] = ypsm[N + k]; }
     }
-    if (outer < P.max_outer) { ++outer; goto L_outer_begin; }
+    if (CS->outer < P.max_outer) { CS->outer = CS->outer + 1; goto L_outer_begin; }
     goto L_finish;
 }
 
 L_finish:
-    if (!failed && n_outer == P.max_outer) status = MPCB_NOT_CONVERGED_ITERATIONS;
+    if (!CS->failed && CS->n_outer == P.max_outer) CS->status = MPCB_NOT_CONVERGED_ITERATIONS;
     MPCB_FORJ {
         const int k = lane + 32 * j;
         if (act[j]) {
@@ -517,15 +585,15 @@ L_finish:
         }
     }
     if (lane == 0) {
-        io.exit_status[b] = status;
-        if (io.cost) io.cost[b] = failed ? __longlong_as_double(0x7ff8000000000000LL) : fcost;
-        if (io.n_outer) io.n_outer[b] = n_outer;
-        if (io.n_inner) io.n_inner[b] = inner_total;
-        if (io.fpr) io.fpr[b] = last_fpr;
-        if (io.f1_infeas) io.f1_infeas[b] = dy_plus / I.c;
-        if (io.f2_norm) io.f2_norm[b] = f2n_plus;
-        if (io.penalty) io.penalty[b] = I.c;
-        if (io.evals) { io.evals[2 * b] = I.n_cost; io.evals[2 * b + 1] = I.n_grad; }
+        io.exit_status[b] = CS->status;
+        if (io.cost) io.cost[b] = CS->failed ? __longlong_as_double(0x7ff8000000000000LL) : CS->fcost;
+        if (io.n_outer) io.n_outer[b] = CS->n_outer;
+        if (io.n_inner) io.n_inner[b] = CS->inner_total;
+        if (io.fpr) io.fpr[b] = CS->last_fpr;
+        if (io.f1_infeas) io.f1_infeas[b] = CS->dy_plus / CS->c;
+        if (io.f2_norm) io.f2_norm[b] = CS->f2n_plus;
+        if (io.penalty) io.penalty[b] = CS->c;
+        if (io.evals) { io.evals[2 * b] = CS->n_cost; io.evals[2 * b + 1] = CS->n_grad; }
     }
     if (MODE != 0) goto L_fetch;
 }
