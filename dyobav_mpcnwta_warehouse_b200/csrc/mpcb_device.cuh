@@ -153,7 +153,11 @@ struct LayV {
 // Cody-Waite reduction by pi/2 (two constants, exact first product for
 // |n| < 2^20) + the fdlibm __kernel_sin/__kernel_cos polynomials in Horner
 // form.  |error| ~ 1 ulp for |x| < 1e5; identical code in the laned oracle.
-__host__ __device__ MPCB_HELPER_ATTR void sincos_cw(double x, double* sn, double* cs)
+#ifndef MPCB_SINCOS_ATTR
+#define MPCB_SINCOS_ATTR __forceinline__
+#endif
+struct SinCos { double s, c; };
+__host__ __device__ MPCB_SINCOS_ATTR SinCos sincos_cw_v(double x)
 {
     const double fn = rint(x * 6.36619772367581382433e-01);
     double r = fma(-fn, 1.57079632673412561417e+00, x);
@@ -174,8 +178,15 @@ __host__ __device__ MPCB_HELPER_ATTR void sincos_cw(double x, double* sn, double
     const int q = static_cast<int>(fn) & 3;
     const double s1 = (q & 1) ? c : s;
     const double c1 = (q & 1) ? s : c;
-    *sn = (q & 2) ? -s1 : s1;
-    *cs = ((q + 1) & 2) ? -c1 : c1;
+    SinCos o;
+    o.s = (q & 2) ? -s1 : s1;
+    o.c = ((q + 1) & 2) ? -c1 : c1;
+    return o;
+}
+__host__ __device__ __forceinline__ void sincos_cw(double x, double* sn, double* cs)
+{
+    const SinCos o = sincos_cw_v(x);
+    *sn = o.s; *cs = o.c;
 }
 
 // ---------------------------------------------------------------- scalar helpers

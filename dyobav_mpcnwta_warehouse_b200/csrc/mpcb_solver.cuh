@@ -46,11 +46,13 @@ template <int SPL>
 struct Inst {   // per-lane slice of the solver state of one instance
     double u0[SPL], u1[SPL];       // iterate (v_k, w_k)
     double g0[SPL], g1[SPL];       // gradient_u
-    double gp0[SPL], gp1[SPL];     // gradient_u_previous
+    // gradient_u_previous is not stored: at its only use (the AKKT residual at the top of a
+    // step) it equals gradient_u from the second step on, and zero at the first
     double h0[SPL], h1[SPL];       // u_half_step
     double r0[SPL], r1[SPL];       // gamma_fpr
     double d0[SPL], d1[SPL];       // direction_lbfgs
-    double s0[SPL], s1[SPL];       // gradient_step
+    // gradient_step u - gamma*grad is recomputed where the line search needs it (same operands,
+    // same bits) instead of being kept
     double ya[SPL], yw[SPL];       // Lagrange multipliers of (acc_k, wacc_k) / max(c, 1); y itself
                                    // lives in the warp's shared-memory scratch
     double gamma, sigma, Lc, cost, norm_r;
@@ -67,10 +69,10 @@ struct ColdState {
     int failed, qscan, pad[2];     // sizeof == 112: keeps the scratch a whole number of double2
 };
 // doubles of per-warp scratch after the L-BFGS rows: y, y+ (2N each), the parked solver vectors
-// (9 x (v, w) per horizon step), the parked PANOC scalars and the cold state
+// (7 x (v, w) per horizon step), the parked PANOC scalars and the cold state
 __host__ __device__ constexpr int scratch_doubles(int N)
 {
-    return 4 * N + 9 * 2 * N + 16 + (int)(sizeof(ColdState) / 8);
+    return 4 * N + 7 * 2 * N + 16 + (int)(sizeof(ColdState) / 8);
 }
 
 #define MPCB_FORJ _Pragma("unroll") for (int j = 0; j < SPL; ++j)
@@ -98,11 +100,12 @@ template <int SPL>
 __device__ __forceinline__ void grad_and_half_step(const KParams& P, Inst<SPL>& I,
                                                    const double (&p0)[SPL], const double (&p1)[SPL])
 {
+    double s0[SPL], s1[SPL];
     MPCB_FORJ {
-        I.s0[j] = fma(-I.gamma, I.g0[j], p0[j]);
-        I.s1[j] = fma(-I.gamma, I.g1[j], p1[j]);
+        s0[j] = fma(-I.gamma, I.g0[j], p0[j]);
+        s1[j] = fma(-I.gamma, I.g1[j], p1[j]);
     }
-    project_U<SPL>(P, I.s0, I.s1, I.h0, I.h1);
+    project_U<SPL>(P, s0, s1, I.h0, I.h1);
 }
 
 // lbfgs crate: update_hessian(g = gamma_fpr, s = u)
@@ -237,7 +240,7 @@ __device__ __forceinline__ void solve_worker(const KParams& P, const double* __r
     // solver's vectors and most of its scalars are parked in shared memory: no spills inside the
     // evaluation's loops, and room for more resident warps per SM.
     double2* const vpark = reinterpret_cast<double2*>(ypsm + 2 * N);
-    double* const spark = reinterpret_cast<double*>(vpark + 9 * N);
+    double* const spark = reinterpret_cast<double*>(vpark + 7 * N);
     ColdState* const CS = reinterpret_cast<ColdState*>(spark + 16);
 #define MPCB_PARK_V(idx, a0, a1) MPCB_FORJ { if (act[j]) vpark[(idx) * N + lane + 32 * j] = make_double2(a0[j], a1[j]); }
 #define MPCB_FILL_V(idx, a0, a1) MPCB_FORJ { if (act[j]) { const double2 t_ = vpark[(idx) * N + lane + 32 * j]; a0[j] = t_.x; a1[j] = t_.y; } }
@@ -285,9 +288,9 @@ L_fetch:
     MPCB_FORJ {
         const int k = lane + 32 * j;
         I.u0[j] = 0.0; I.u1[j] = 0.0; I.ya[j] = 0.0; I.yw[j] = 0.0;
-        I.gp0[j] = 0.0; I.gp1[j] = 0.0; I.g0[j] = 0.0; I.g1[j] = 0.0;
+        I.g0[j] = 0.0; I.g1[j] = 0.0;
         I.h0[j] = 0.0; I.h1[j] = 0.0; I.r0[j] = 0.0; I.r1[j] = 0.0;
-        I.d0[j] = 0.0; I.d1[j] = 0.0; I.s0[j] = 0.0; I.s1[j] = 0.0;
+        I.d0[j] = 0.0; I.d1[j] = 0.0;
         pt0[j] = 0.0; pt1[j] = 0.0;
         if (act[j]) {
             if (io.u0) {
@@ -319,7 +322,6 @@ L_outer_begin:   // ---- AlmOptimizer::step: project y on Y, then the inner prob
         // psi uses y / max(c, 1): constant over the inner problem, divided once here
         I.ya[j] = ya_ / fmax(CS->c, 1.0);
         I.yw[j] = yw_ / fmax(CS->c, 1.0);
-        I.gp0[j] = 0.0; I.gp1[j] = 0.0;   // set_akkt_tolerance zeroes the cached previous gradient
     }
     // PANOCEngine::init
     B.reset();
@@ -329,9 +331,9 @@ L_outer_begin:   // ---- AlmOptimizer::step: project y on Y, then the inner prob
 
 L_eval:
     // park
-    MPCB_PARK_V(0, I.u0, I.u1); MPCB_PARK_V(1, I.g0, I.g1); MPCB_PARK_V(2, I.gp0, I.gp1);
-    MPCB_PARK_V(3, I.h0, I.h1); MPCB_PARK_V(4, I.r0, I.r1); MPCB_PARK_V(5, I.d0, I.d1);
-    MPCB_PARK_V(6, I.s0, I.s1); MPCB_PARK_V(7, B.os0, B.os1); MPCB_PARK_V(8, B.og0, B.og1);
+    MPCB_PARK_V(0, I.u0, I.u1); MPCB_PARK_V(1, I.g0, I.g1); MPCB_PARK_V(2, I.h0, I.h1);
+    MPCB_PARK_V(3, I.r0, I.r1); MPCB_PARK_V(4, I.d0, I.d1);
+    MPCB_PARK_V(5, B.os0, B.os1); MPCB_PARK_V(6, B.og0, B.og1);
     spark[0] = I.sigma; spark[1] = I.Lc; spark[2] = I.norm_r; spark[3] = cost_half;
     spark[4] = rhs_ls; spark[5] = tau; spark[6] = B.gamma;
     reinterpret_cast<int*>(spark + 8)[0] = num_iter;
@@ -342,13 +344,13 @@ L_eval:
     eval_psi<SPL, FIXED>(P, S, pt0, pt1, ceff, I.ya, I.yw, want_grad, o, lane);
     // un-park (inactive lanes hold zeros in every vector)
     MPCB_FORJ {
-        I.u0[j] = 0.0; I.u1[j] = 0.0; I.g0[j] = 0.0; I.g1[j] = 0.0; I.gp0[j] = 0.0; I.gp1[j] = 0.0;
+        I.u0[j] = 0.0; I.u1[j] = 0.0; I.g0[j] = 0.0; I.g1[j] = 0.0;
         I.h0[j] = 0.0; I.h1[j] = 0.0; I.r0[j] = 0.0; I.r1[j] = 0.0; I.d0[j] = 0.0; I.d1[j] = 0.0;
-        I.s0[j] = 0.0; I.s1[j] = 0.0; B.os0[j] = 0.0; B.os1[j] = 0.0; B.og0[j] = 0.0; B.og1[j] = 0.0;
+        B.os0[j] = 0.0; B.os1[j] = 0.0; B.og0[j] = 0.0; B.og1[j] = 0.0;
     }
-    MPCB_FILL_V(0, I.u0, I.u1); MPCB_FILL_V(1, I.g0, I.g1); MPCB_FILL_V(2, I.gp0, I.gp1);
-    MPCB_FILL_V(3, I.h0, I.h1); MPCB_FILL_V(4, I.r0, I.r1); MPCB_FILL_V(5, I.d0, I.d1);
-    MPCB_FILL_V(6, I.s0, I.s1); MPCB_FILL_V(7, B.os0, B.os1); MPCB_FILL_V(8, B.og0, B.og1);
+    MPCB_FILL_V(0, I.u0, I.u1); MPCB_FILL_V(1, I.g0, I.g1); MPCB_FILL_V(2, I.h0, I.h1);
+    MPCB_FILL_V(3, I.r0, I.r1); MPCB_FILL_V(4, I.d0, I.d1);
+    MPCB_FILL_V(5, B.os0, B.os1); MPCB_FILL_V(6, B.og0, B.og1);
     I.sigma = spark[0]; I.Lc = spark[1]; I.norm_r = spark[2]; cost_half = spark[3];
     rhs_ls = spark[4]; tau = spark[5]; B.gamma = spark[6];
     num_iter = reinterpret_cast<int*>(spark + 8)[0];
@@ -395,13 +397,13 @@ H_INIT_LIP: {
 }
 
 L_step_begin:   // ---- PANOCEngine::step
-    if (I.iter >= 1) { MPCB_FORJ { I.gp0[j] = I.g0[j]; I.gp1[j] = I.g1[j]; } }
     compute_fpr<SPL>(I);
     if (I.norm_r < P.tol) {
         double a = 0.0;
         MPCB_FORJ {
-            const double t0 = ddiv(I.r0[j], I.gamma) + I.g0[j] - I.gp0[j];
-            const double t1 = ddiv(I.r1[j], I.gamma) + I.g1[j] - I.gp1[j];
+            // gradient_u_previous: a copy of gradient_u once a step has been taken, zero before
+            const double t0 = ddiv(I.r0[j], I.gamma) + I.g0[j] - (I.iter >= 1 ? I.g0[j] : 0.0);
+            const double t1 = ddiv(I.r1[j], I.gamma) + I.g1[j] - (I.iter >= 1 ? I.g1[j] : 0.0);
             a = fma(t0, t0, fma(t1, t1, a));
         }
         if (dsqrt(warp_sum(a)) < CS->akkt_tol) { flag = false; goto L_step_return; }
@@ -456,8 +458,8 @@ L_lip_check: {
     }
     // linesearch on the forward-backward envelope
     double dd = 0.0;
-    MPCB_FORJ {
-        const double e0 = I.s0[j] - I.h0[j], e1 = I.s1[j] - I.h1[j];
+    MPCB_FORJ {   // gradient step of the current iterate: the operands it was last computed from
+        const double e0 = fma(-I.gamma, I.g0[j], I.u0[j]) - I.h0[j], e1 = fma(-I.gamma, I.g1[j], I.u1[j]) - I.h1[j];
         dd = fma(e0, e0, fma(e1, e1, dd));
     }
     const double dist2 = warp_sum(dd);
@@ -485,7 +487,7 @@ H_LS: {
     grad_and_half_step<SPL>(P, I, pt0, pt1);
     double d2 = 0.0;
     MPCB_FORJ {
-        const double e0 = I.s0[j] - I.h0[j], e1 = I.s1[j] - I.h1[j];
+        const double e0 = fma(-I.gamma, I.g0[j], pt0[j]) - I.h0[j], e1 = fma(-I.gamma, I.g1[j], pt1[j]) - I.h1[j];
         d2 = fma(e0, e0, fma(e1, e1, d2));
     }
     d2 = warp_sum(d2);
