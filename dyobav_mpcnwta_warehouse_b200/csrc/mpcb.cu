@@ -128,6 +128,10 @@ __global__ void __launch_bounds__(128) stage_kernel(const KParams P, const doubl
             S[L.o_seg + 2 * N + k] = dx;
             S[L.o_seg + 3 * N + k] = dy;
             S[L.o_seg + 4 * N + k] = 1.0 / (dx * dx + dy * dy + 1e-16);
+            // unit tangent, shortened so that |t| <= 1 survives rounding (zero for a padded segment)
+            const double dl = sqrt(dx * dx + dy * dy);
+            S[L.o_seg + 5 * N + k] = dl > 1e-9 ? dx / dl * (1.0 - 1e-9) : 0.0;
+            S[L.o_seg + 6 * N + k] = dl > 1e-9 ? dy / dl * (1.0 - 1e-9) : 0.0;
         }
         for (int r = tid; r < L.Nother; r += nt) {
             S[L.o_c0 + r] = pr[L.p_c0 + 3 * r];
@@ -219,6 +223,17 @@ __global__ void __launch_bounds__(128) stage_kernel(const KParams P, const doubl
                 const double vx = t * ddx - ex, vy = t * ddy - ey;
                 run = fmin(run, sqrt(vx * vx + vy * vy));
                 MG[L.f_seg + k * N + i] = margin_f(run, 0.0);
+            }
+            // directional twin: the projection on t_k is linear along a segment, so its minimum
+            // over a segment sits at an end point
+            const double tx = sg[5 * N + k], ty = sg[6 * N + k];
+            double run2 = INFINITY;
+            for (int i = N - 1; i >= 0; --i) {
+                const double ex = sg[i] - ax, ey = sg[N + i] - ay;
+                const double p0 = ex * tx + ey * ty;
+                const double p1 = (ex + sg[2 * N + i]) * tx + (ey + sg[3 * N + i]) * ty;
+                run2 = fmin(run2, fmin(p0, p1));
+                MG[L.f_seg2 + k * N + i] = margin_f(run2, 0.0);
             }
         }
         __syncthreads();

@@ -56,6 +56,8 @@ struct Lay {            // offsets (in doubles) inside one staged scenario block
     int f_imin;         // per-item minimum over the steps: [Ndyn] ellipses (both slots), then
                         // [Nstc] polygons, [Nother] robots at t=0, [Nother] predicted robots
     int f_seg;          // [N][N]: (k, i) -> min over segments i' >= i of dist(A_k, segment i')
+    int f_seg2;         // [N][N]: (k, i) -> min over segments i' >= i of (x - A_k).t_k, x on the segment,
+                        // t_k the (slightly shortened) unit tangent of segment k: a directional bound
     int total;          // doubles, multiple of 2 (16-byte granularity for TMA bulk copies)
     int np;             // length of a raw parameter row
     // raw p offsets (mpc_builder.py:47-60)
@@ -84,7 +86,7 @@ __host__ __device__ constexpr Lay make_lay(int N, int Nother, int Nstc, int nedg
     L.o_hdr = o;  o += H_SIZE;
     L.o_rv = o;   o += N;
     L.o_qstc = o; o += N;
-    L.o_seg = o;  o += 5 * N;
+    L.o_seg = o;  o += 7 * N;   // s1x, s1y, dx, dy, 1/(|d|^2+1e-16), tangent x, y
     L.o_c0 = o;   o += 2 * Nother;
     L.o_c = o;    o += 2 * Nother * N;
     L.o_poly = o; o += 3 * nedge * Nstc;
@@ -99,6 +101,7 @@ __host__ __device__ constexpr Lay make_lay(int N, int Nother, int Nstc, int nedg
     L.f_c = fo;    fo += Nother * N;
     L.f_imin = fo; fo += Ndyn + Nstc + 2 * Nother;
     L.f_seg = fo;  fo += N * N;
+    L.f_seg2 = fo; fo += N * N;
     o += (fo + 1) / 2;
     L.total = (o + 1) & ~1;
     int q = 0;
@@ -144,7 +147,7 @@ struct LayV {
     MPCB_LAYF(N) MPCB_LAYF(Nother) MPCB_LAYF(Nstc) MPCB_LAYF(nedge) MPCB_LAYF(Ndyn)
     MPCB_LAYF(o_hdr) MPCB_LAYF(o_rv) MPCB_LAYF(o_qstc) MPCB_LAYF(o_seg) MPCB_LAYF(o_c0) MPCB_LAYF(o_c)
     MPCB_LAYF(o_poly) MPCB_LAYF(o_e0) MPCB_LAYF(o_et) MPCB_LAYF(o_mg)
-    MPCB_LAYF(f_e0) MPCB_LAYF(f_et) MPCB_LAYF(f_poly) MPCB_LAYF(f_c0) MPCB_LAYF(f_c) MPCB_LAYF(f_imin) MPCB_LAYF(f_seg)
+    MPCB_LAYF(f_e0) MPCB_LAYF(f_et) MPCB_LAYF(f_poly) MPCB_LAYF(f_c0) MPCB_LAYF(f_c) MPCB_LAYF(f_imin) MPCB_LAYF(f_seg) MPCB_LAYF(f_seg2)
     MPCB_LAYF(total)
 #undef MPCB_LAYF
 };
@@ -459,7 +462,7 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
     double gx[SPL], gy[SPL], gvd[SPL], gwd[SPL];
     double Spoly[SPL], dSx[SPL], dSy[SPL];
     double X[SPL], Y[SPL];
-    float Df[SPL];
+    float Df[SPL], Pf[SPL];
     bool anyhinge = false;
     unsigned hm[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};   // obstacles whose raw hinge is positive (Ndyn <= 256)
     const double* sg = S + L.o_seg();
@@ -477,6 +480,11 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
             const double ax = X[j] - sg[k], ay = Y[j] - sg[N + k];
             Df[j] = CULL ? __double2float_ru(fma(dsqrt(fma(ax, ax, ay * ay)), 1.0 + 1e-9, 1e-9))
                          : __int_as_float(0x7f800000);
+            // how far the robot is AHEAD of the anchor along the path tangent, rounded up: a later
+            // segment whose every point projects further ahead than that by more than the current
+            // best distance cannot be the minimum (the lagging robot's walk stops after one segment)
+            const double pr = fma(ax, sg[5 * N + k], ay * sg[6 * N + k]);
+            Pf[j] = CULL ? __double2float_ru(fma(fabs(pr), 1e-9, pr) + 1e-9) : __int_as_float(0x7f800000);
             if (act[j]) {
                 dmax = fmaxf(dmax, Df[j]);
                 bad |= !(Df[j] < __int_as_float(0x7f800000));
@@ -503,6 +511,8 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
         //    says no later segment can beat the current minimum.
         {
             const float* tm = MG + L.f_seg() + k * N;
+            const float* tm2 = MG + L.f_seg2() + k * N;
+            const float Pj = Pf[j];
             double best = INFINITY;
             int ib = k;
             bool alive = true;
@@ -511,7 +521,7 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
                 if (alive) {
                     if (i >= N) { alive = false; }
                     else {
-                        const float lb = tm[i] - D;
+                        const float lb = fmaxf(tm[i] - D, tm2[i] - Pj);
                         if (lb > 0.f && (double)lb * (double)lb * (1.0 - 1e-6) > best) { alive = false; }
                         else {
                             const double ex = x - sg[i], ey = y - sg[N + i];
