@@ -30,9 +30,17 @@
 #define MPCB_QTHREADS_FIXED 512   // 16 warps x 128 registers (solver state parked in shared memory during the
                                   // evaluation, per-CTA queues keep L1 on 2-3 scenario blocks): best measured
 #endif
+#ifndef MPCB_QTHREADS_FIXED2
+#define MPCB_QTHREADS_FIXED2 384  // 40 ellipses: 148 registers without spills, 12 warps
+#endif
 #ifndef MPCB_MIN_CTAS
 #define MPCB_MIN_CTAS 1
 #endif
+// threads per CTA of the queue kernel for a compiled-in dimension set (0: run-time dims)
+constexpr int qthreads(int fixed)
+{
+    return fixed == 1 ? MPCB_QTHREADS_FIXED : fixed == 2 ? MPCB_QTHREADS_FIXED2 : MPCB_QTHREADS;
+}
 using namespace mpcb;
 
 namespace {
@@ -399,7 +407,7 @@ __global__ void __launch_bounds__(256) solve_kernel(const KParams P, const doubl
 // slow instance never holds other warps at a CTA barrier; scenario blocks are read from the
 // staged copy in global memory (L1/L2-resident: with culling a solve touches a few KB of it).
 template <int SPL, int FIXED>
-__global__ void __launch_bounds__(FIXED == 1 ? MPCB_QTHREADS_FIXED : MPCB_QTHREADS, MPCB_MIN_CTAS) solve_kernel_queue(const KParams P, const double* __restrict__ staged,
+__global__ void __launch_bounds__(qthreads(FIXED), MPCB_MIN_CTAS) solve_kernel_queue(const KParams P, const double* __restrict__ staged,
                                                           const SolveIO io, int* __restrict__ counter)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -518,7 +526,7 @@ int make_plan(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solver_cfg* c,
                     d->Ndyn == F.Ndyn)
                     pl.fixed = fx;
             }
-        const int maxw = (pl.fixed == 1 ? MPCB_QTHREADS_FIXED : MPCB_QTHREADS) / 32;
+        const int maxw = qthreads(pl.fixed) / 32;
         P.warps = env_int("MPCB_WARPS", maxw); P.nsc = 0;
         if (P.warps < 1 || P.warps > maxw) P.warps = maxw < 8 ? maxw : 8;
         while (P.warps > 1 && 16 + P.warps * lbw > cap) --P.warps;   // large N: fewer warps per CTA
