@@ -463,8 +463,7 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
     double Spoly[SPL], dSx[SPL], dSy[SPL];
     double X[SPL], Y[SPL];
     float Df[SPL], Pf[SPL];
-    bool anyhinge = false;
-    unsigned hm[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};   // obstacles whose raw hinge is positive (Ndyn <= 256)
+    double cstj[SPL];      // stage cost of the lane's step in row j
     const double* sg = S + L.o_seg();
 
     // positions and, per step, the distance to the step's anchor (its reference point),
@@ -478,7 +477,9 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
             X[j] = H[H_S0X] + px[j];
             Y[j] = H[H_S0Y] + py[j];
             const double ax = X[j] - sg[k], ay = Y[j] - sg[N + k];
-            Df[j] = CULL ? __double2float_ru(fma(dsqrt(fma(ax, ax, ay * ay)), 1.0 + 1e-9, 1e-9))
+            // upper bound of |p - A_k| in float: every step rounds up (the double square is inflated
+            // past its own rounding first), so three instructions replace an IEEE double sqrt
+            Df[j] = CULL ? __fsqrt_ru(__double2float_ru(fma(ax, ax, ay * ay) * (1.0 + 1e-9)))
                          : __int_as_float(0x7f800000);
             // how far the robot is AHEAD of the anchor along the path tangent, rounded up: a later
             // segment whose every point projects further ahead than that by more than the current
@@ -628,45 +629,102 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
                 }
             }
         }
-        // -- dynamic ellipses: t=0 slot (broadcast) and t=k+1 slot (mpc_builder.py:111-143)
-        bool hinge = sp > 0.0;
-        {
-            const double* e0 = S + L.o_e0();
-            const double* et = S + L.o_et() + k;
-            const float* me0 = MG + L.f_e0() + k;
-            const float* met = MG + L.f_et() + k;
+        // inactive lanes (steps beyond the horizon) carry no polygon hinge into F2
+        cstj[j] = cst;
+        gx[j] = ggx; gy[j] = ggy;
+        Spoly[j] = act[j] ? sp : 0.0; dSx[j] = act[j] ? spx : 0.0; dSy[j] = act[j] ? spy : 0.0;
+    }
+
+    // ---- dynamic ellipses (mpc_builder.py:111-143) and the penalty constraints F2
+    //      (mpc_builder.py:72,106,119,137: vector of Ndyn, the polygon hinge sum SP broadcast
+    //      into every entry), in ONE walk over the candidate obstacles: every lane visits obstacle
+    //      i at the same time, so F2_i = SP + sum over steps of the raw hinges is reduced right
+    //      where the hinges are computed and the second evaluation pass of earlier versions is
+    //      gone.  F2's gradient terms go to their own accumulator (fx, fy), added to the cost
+    //      gradient once at the end, so the order of the cost-gradient sum does not depend on
+    //      which obstacles are hit.
+    double f2sq = 0.0, sumF2 = 0.0;
+    double fx[SPL], fy[SPL];
+    bool anyF2;     // whether any entry of F2 can be non-zero or is wanted
+    {
+        double spl = 0.0;
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) { spl += Spoly[j]; fx[j] = 0.0; fy[j] = 0.0; }
+        const bool anyp = __any_sync(FULL, spl > 0.0);
+        const double SP = anyp ? warp_sum(spl) : 0.0;
+        anyF2 = anyp || F2out != nullptr;
+        int nxt = 0;     // F2 entries [0, nxt) are accounted for
+        const double* e0 = S + L.o_e0();
+        const double* etb = S + L.o_et();
+        const float* me0b = MG + L.f_e0();
+        const float* metb = MG + L.f_et();
 #pragma unroll 1
-            for (int base = 0; base < L.Ndyn(); base += 32) {
-                const int it = base + lane;
-                unsigned mk = __ballot_sync(FULL, it < L.Ndyn() && !(IM_E[it < L.Ndyn() ? it : 0] > dmax));
-                while (mk) {
-                    const int bit = __ffs(mk) - 1;
-                    const int i = base + bit;
-                    mk &= mk - 1;
-                    bool hit = false;
-                    if (!(me0[i * N] > D)) {
-                        EllT a;
-                        ellipse_terms(GRAD, e0 + i, L.Ndyn(), x, y, a);
-                        cst += a.cost;
-                        if (GRAD) { ggx += a.gx; ggy += a.gy; }
-                        hit |= a.hr > 0.0;
+        for (int base = 0; base < L.Ndyn(); base += 32) {
+            const int it = base + lane;
+            unsigned mk = __ballot_sync(FULL, it < L.Ndyn() && !(IM_E[it < L.Ndyn() ? it : 0] > dmax));
+            while (mk) {
+                const int i = base + __ffs(mk) - 1;
+                mk &= mk - 1;
+                EllT a[SPL], b[SPL];
+                double hl = 0.0;
+#pragma unroll
+                for (int j = 0; j < SPL; ++j) {
+                    const int k = act[j] ? kk[j] : N - 1;
+                    a[j].hr = 0.0; b[j].hr = 0.0;
+                    if (!(me0b[i * N + k] > Df[j])) {          // t = 0 slot (one ellipse for all steps)
+                        ellipse_terms(GRAD, e0 + i, L.Ndyn(), X[j], Y[j], a[j]);
+                        cstj[j] += a[j].cost;
+                        if (GRAD) { gx[j] += a[j].gx; gy[j] += a[j].gy; }
                     }
-                    if (!(met[i * N] > D)) {
-                        EllT b;
-                        ellipse_terms(GRAD, et + i * N, L.Ndyn() * N, x, y, b);
-                        cst += b.cost;
-                        if (GRAD) { ggx += b.gx; ggy += b.gy; }
-                        hit |= b.hr > 0.0;
+                    if (!(metb[i * N + k] > Df[j])) {          // t = k+1 slot
+                        ellipse_terms(GRAD, etb + k + i * N, L.Ndyn() * N, X[j], Y[j], b[j]);
+                        cstj[j] += b[j].cost;
+                        if (GRAD) { gx[j] += b[j].gx; gy[j] += b[j].gy; }
                     }
-                    if (hit && act[j]) { hm[(base >> 5) & 7] |= 1u << bit; hinge = true; }
+                    if (!act[j]) { a[j].hr = 0.0; b[j].hr = 0.0; }
+                    hl += a[j].hr + b[j].hr;
+                }
+                if (__any_sync(FULL, hl > 0.0)) {
+#pragma unroll 1
+                    for (; nxt < i; ++nxt) {                   // entries without a hinge equal SP
+                        if (F2out && lane == 0) F2out[nxt] = SP;
+                        f2sq = fma(SP, SP, f2sq);
+                        sumF2 += SP;
+                    }
+                    const double F2i = SP + warp_sum(hl);
+                    if (F2out && lane == 0) F2out[i] = F2i;
+                    f2sq = fma(F2i, F2i, f2sq);
+                    sumF2 += F2i;
+                    nxt = i + 1;
+                    anyF2 = true;
+                    if (GRAD && F2i > 0.0) {
+                        const double m = c * F2i;
+#pragma unroll
+                        for (int j = 0; j < SPL; ++j) {
+                            if (a[j].hr > 0.0) { fx[j] = fma(m, a[j].hrx, fx[j]); fy[j] = fma(m, a[j].hry, fy[j]); }
+                            if (b[j].hr > 0.0) { fx[j] = fma(m, b[j].hrx, fx[j]); fy[j] = fma(m, b[j].hry, fy[j]); }
+                        }
+                    }
                 }
             }
         }
-        if (!act[j]) { cst = 0.0; ggx = 0.0; ggy = 0.0; sp = 0.0; spx = 0.0; spy = 0.0; hinge = false; gvd[j] = 0.0; gwd[j] = 0.0; }
-        cost += cst;
-        gx[j] = ggx; gy[j] = ggy;
-        Spoly[j] = sp; dSx[j] = spx; dSy[j] = spy;
-        anyhinge |= hinge;
+        if (L.Ndyn() == 0) {
+            f2sq = SP * SP;
+            sumF2 = SP;
+            if (F2out && lane == 0) F2out[0] = SP;
+        } else if (anyF2) {
+#pragma unroll 1
+            for (; nxt < L.Ndyn(); ++nxt) {
+                if (F2out && lane == 0) F2out[nxt] = SP;
+                f2sq = fma(SP, SP, f2sq);
+                sumF2 += SP;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+        if (!act[j]) { cstj[j] = 0.0; gx[j] = 0.0; gy[j] = 0.0; gvd[j] = 0.0; gwd[j] = 0.0; }
+        cost += cstj[j];
     }
 
     // ---- terminal cost on the last state (mpc_builder.py:148)
@@ -686,65 +744,14 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
         }
     }
 
-    // ---- penalty constraints F2 (mpc_builder.py:72,106,119,137; vector of Ndyn
-    //      with the polygon hinge broadcast into every entry)
-    double f2sq = 0.0;
-    if (__any_sync(FULL, anyhinge) || F2out != nullptr) {
-        double spl = 0.0;
+    // ---- F2's share of the gradient: the ellipse hinges collected above, then the polygon
+    //      hinges (their sum enters every entry of F2)
+    if (GRAD && anyF2) {
+        const double m = c * sumF2;
 #pragma unroll
-        for (int j = 0; j < SPL; ++j) spl += Spoly[j];
-        const double SP = warp_sum(spl);
-        double sumF2 = 0.0;
-        if (L.Ndyn() == 0) {
-            f2sq = SP * SP;
-            sumF2 = SP;
-            if (F2out && lane == 0) F2out[0] = SP;
-        }
-#pragma unroll 1
-        for (int base = 0; base < L.Ndyn(); base += 32) {
-            // only obstacles whose raw hinge was positive for some step (pass A) can differ from SP
-            const unsigned mk = __reduce_or_sync(FULL, hm[(base >> 5) & 7]);
-            const int lim = L.Ndyn() - base < 32 ? L.Ndyn() - base : 32;
-#pragma unroll 1
-            for (int bi = 0; bi < lim; ++bi) {
-                const int i = base + bi;
-                double F2i = SP;
-                EllT a[SPL], b[SPL];
-                const bool cand = (mk >> bi) & 1u;
-                if (cand) {     // an obstacle outside the mask cannot have a positive hinge
-                    double hl = 0.0;
-#pragma unroll
-                    for (int j = 0; j < SPL; ++j) {
-                        const int k = act[j] ? kk[j] : N - 1;
-                        a[j].hr = 0.0; b[j].hr = 0.0;
-                        if (act[j] && !(MG[L.f_e0() + i * N + k] > Df[j]))
-                            ellipse_terms(GRAD, S + L.o_e0() + i, L.Ndyn(), X[j], Y[j], a[j]);
-                        if (act[j] && !(MG[L.f_et() + i * N + k] > Df[j]))
-                            ellipse_terms(GRAD, S + L.o_et() + k + i * N, L.Ndyn() * N, X[j], Y[j], b[j]);
-                        hl += a[j].hr + b[j].hr;
-                    }
-                    if (__any_sync(FULL, hl > 0.0)) F2i += warp_sum(hl);
-                }
-                if (F2out && lane == 0) F2out[i] = F2i;
-                f2sq = fma(F2i, F2i, f2sq);
-                sumF2 += F2i;
-                if (cand && GRAD && F2i > 0.0) {
-                    const double m = c * F2i;
-#pragma unroll
-                    for (int j = 0; j < SPL; ++j) {
-                        if (a[j].hr > 0.0) { gx[j] = fma(m, a[j].hrx, gx[j]); gy[j] = fma(m, a[j].hry, gy[j]); }
-                        if (b[j].hr > 0.0) { gx[j] = fma(m, b[j].hrx, gx[j]); gy[j] = fma(m, b[j].hry, gy[j]); }
-                    }
-                }
-            }
-        }
-        if (GRAD) {
-            const double m = c * sumF2;
-#pragma unroll
-            for (int j = 0; j < SPL; ++j) {
-                gx[j] = fma(m, dSx[j], gx[j]);
-                gy[j] = fma(m, dSy[j], gy[j]);
-            }
+        for (int j = 0; j < SPL; ++j) {
+            gx[j] = fma(m, dSx[j], gx[j] + fx[j]);
+            gy[j] = fma(m, dSy[j], gy[j] + fy[j]);
         }
     }
 

@@ -460,6 +460,12 @@ static void eval_psi(const scen_t* S, lanes_t v, lanes_t w, double c, lanes_t ya
         }
         const double SP = warp_sum(spl);
         double sumF2 = 0.0;
+        /* F2's gradient terms are collected in their own accumulator and added to the cost
+           gradient once, as the kernel does (it meets the hinges while it is still summing
+           the ellipse cost terms) */
+        lanes_t fx, fy;
+        for (int j = 0; j < J; ++j)
+            for (int l = 0; l < W; ++l) { fx[j][l] = 0.0; fy[j][l] = 0.0; }
         if (S->Ndyn == 0) {
             f2sq = SP * SP;
             sumF2 = SP;
@@ -492,8 +498,8 @@ static void eval_psi(const scen_t* S, lanes_t v, lanes_t w, double c, lanes_t ya
                 const double m = c * F2i;
                 for (int j = 0; j < J; ++j)
                     for (int l = 0; l < W; ++l) {
-                        if (A[j][l].hr > 0.0) { gx[j][l] = fma(m, A[j][l].hrx, gx[j][l]); gy[j][l] = fma(m, A[j][l].hry, gy[j][l]); }
-                        if (B[j][l].hr > 0.0) { gx[j][l] = fma(m, B[j][l].hrx, gx[j][l]); gy[j][l] = fma(m, B[j][l].hry, gy[j][l]); }
+                        if (A[j][l].hr > 0.0) { fx[j][l] = fma(m, A[j][l].hrx, fx[j][l]); fy[j][l] = fma(m, A[j][l].hry, fy[j][l]); }
+                        if (B[j][l].hr > 0.0) { fx[j][l] = fma(m, B[j][l].hrx, fx[j][l]); fy[j][l] = fma(m, B[j][l].hry, fy[j][l]); }
                     }
             }
         }
@@ -501,8 +507,8 @@ static void eval_psi(const scen_t* S, lanes_t v, lanes_t w, double c, lanes_t ya
             const double m = c * sumF2;
             for (int j = 0; j < J; ++j)
                 for (int l = 0; l < W; ++l) {
-                    gx[j][l] = fma(m, dSx[j][l], gx[j][l]);
-                    gy[j][l] = fma(m, dSy[j][l], gy[j][l]);
+                    gx[j][l] = fma(m, dSx[j][l], gx[j][l] + fx[j][l]);
+                    gy[j][l] = fma(m, dSy[j][l], gy[j][l] + fy[j][l]);
                 }
         }
     }
