@@ -207,6 +207,16 @@ __device__ __forceinline__ double div_nonneg(double x, double g)
     return ddiv(x, g);
 }
 
+// x / g where x is often exactly zero (fixed-point residual of the steps past the horizon and of
+// saturated inputs): zero lanes divide 1 by g instead and keep their (signed) zero, so the warp
+// stays off the division's slow path; +-0 / g is +-0 for any finite g > 0.
+__device__ __forceinline__ double div_maybe_zero(double x, double g)
+{
+    const bool z = x == 0.0 && g > 0.0 && g < INFINITY;
+    const double q = ddiv(z ? 1.0 : x, g);
+    return z ? x : q;
+}
+
 // max(0, r) and clamp to [0, 1] as plain selects (NaN -> 0, like fmax/fmin; a few instructions
 // instead of the library forms' NaN/signed-zero handling).  Same code in the laned oracle.
 __host__ __device__ __forceinline__ double pos_part(double r) { return r > 0.0 ? r : 0.0; }

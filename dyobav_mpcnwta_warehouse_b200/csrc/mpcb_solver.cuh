@@ -402,8 +402,8 @@ L_step_begin:   // ---- PANOCEngine::step
         double a = 0.0;
         MPCB_FORJ {
             // gradient_u_previous: a copy of gradient_u once a step has been taken, zero before
-            const double t0 = ddiv(I.r0[j], I.gamma) + I.g0[j] - (I.iter >= 1 ? I.g0[j] : 0.0);
-            const double t1 = ddiv(I.r1[j], I.gamma) + I.g1[j] - (I.iter >= 1 ? I.g1[j] : 0.0);
+            const double t0 = div_maybe_zero(I.r0[j], I.gamma) + I.g0[j] - (I.iter >= 1 ? I.g0[j] : 0.0);
+            const double t1 = div_maybe_zero(I.r1[j], I.gamma) + I.g1[j] - (I.iter >= 1 ? I.g1[j] : 0.0);
             a = fma(t0, t0, fma(t1, t1, a));
         }
         if (dsqrt(warp_sum(a)) < CS->akkt_tol) { flag = false; goto L_step_return; }
