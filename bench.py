@@ -275,9 +275,10 @@ def main():
         "clocks": clk.summary(),
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp64_peak,
-                     # ncu dram__bytes_read+write of this kernel: 41 030 400 B for 16 384 solves
-                     # (profiles/r1_traffic_metrics.csv) = 2 504 B per solve, scaled to this launch
-                     "traffic": 2504.0 * B,
+                     # ncu dram__bytes_read+write of this kernel: 43 384 064 B for 16 384 solves
+                     # (profiles/r1_traffic_metrics.csv) = 2 648 B per solve,
+                     # scaled to this launch
+                     "traffic": 2648.0 * B,
                      "peak_source": peak_src, "peak_nominal": fp64_nominal,
                      "note": "MEASURED_PEAKS.json holds no FP64 figure, so the FMA pipe is probed in this run "
                              "(nominal 148 SM x 64 FMA/clk x 1.965 GHz = 37.2). achieved = SURVEY 8(d) work "
