@@ -1,0 +1,72 @@
+"""An anchor for the SOLVER half that does not depend on any restatement of PANOC: whatever the
+iteration history, a solve that reports `Converged` must return a point that an independent
+optimiser cannot improve.  The final augmented Lagrangian psi(.; c, y+) is rebuilt from the
+solver's outputs (penalty, multipliers) with the goldens-pinned evaluator
+(oracle.evaluate, reference operation order) and handed to scipy's L-BFGS-B with the input box
+as bounds: starting from the returned u it must stay within the north-star tolerance (1e-4).
+Measured: it moves by <= 1.3e-5 and gains <= 2.5e-6 in psi.  (cross-check 2.)"""
+import numpy as np
+import pytest
+from scipy.optimize import minimize
+
+from dyobav_mpcnwta_warehouse_b200 import Dims, RobotSpec, SolverSettings, instances
+from oracle import oracle
+
+TOL_U = 1e-4      # north-star tolerance on the control sequence
+TOL_PSI = 1e-5
+
+
+def _certify(dims, rb, p, u, y, c):
+    """(max |u_scipy - u|, psi(u) - psi(u_scipy)) for psi(.; c, y) over the input box."""
+    def fun(x):
+        r = oracle.evaluate(dims, rb, p, x, y, c)
+        return r["psi"], r["grad"]
+    lo = np.tile([rb.lin_vel_min, -rb.ang_vel_max], dims.N)
+    hi = np.tile([rb.lin_vel_max, rb.ang_vel_max], dims.N)
+    psi0, _ = fun(u)
+    m = minimize(fun, u, jac=True, method="L-BFGS-B", bounds=list(zip(lo, hi)),
+                 options=dict(maxiter=500, ftol=1e-15, gtol=1e-10, maxcor=20))
+    return float(np.abs(m.x - u).max()), float(psi0 - m.fun)
+
+
+def _check_converged(dims, rb, P, U, Y, C, status, f2n, starts=1, want=6):
+    n_checked = 0
+    for b in range(len(U)):
+        if status[b] != 0:
+            continue
+        u = U[b]
+        assert (u.reshape(-1, 2)[:, 0] >= rb.lin_vel_min).all() and (u.reshape(-1, 2)[:, 0] <= rb.lin_vel_max).all()
+        assert (np.abs(u.reshape(-1, 2)[:, 1]) <= rb.ang_vel_max).all()
+        assert f2n[b] <= 1e-4 + 1e-12                      # penalty constraints met (delta)
+        du, dpsi = _certify(dims, rb, P[b // starts], u, Y[b], float(C[b]))
+        assert du < TOL_U, (b, du)
+        assert dpsi < TOL_PSI, (b, dpsi)
+        n_checked += 1
+    assert n_checked >= want, f"only {n_checked} converged instances in the sample"
+
+
+def test_oracle_converged_solutions_are_local_minimisers():
+    """The CPU oracle (reference operation order)."""
+    dims, rb, cfg = Dims(), RobotSpec(), SolverSettings()
+    P = instances.generate(dims, 24, seed=5)
+    outs = [oracle.solve(dims, rb, cfg, P[i]) for i in range(len(P))]
+    _check_converged(dims, rb, P, [o["u"] for o in outs], [o["y"] for o in outs],
+                     [o["penalty"] for o in outs], [o["exit_status"] for o in outs],
+                     [o["f2_norm"] for o in outs])
+
+
+@pytest.mark.gpu
+def test_gpu_converged_solutions_are_local_minimisers():
+    """The CUDA path: same certificate on what the kernel returns (u, y+, penalty)."""
+    import torch
+    from dyobav_mpcnwta_warehouse_b200.solver import BatchedSolver
+    assert torch.cuda.is_available()
+    dims, rb, cfg = Dims(), RobotSpec(), SolverSettings()
+    n_p, starts = 12, 4
+    P = instances.generate(dims, n_p, seed=5)
+    U0 = instances.multistart_guesses(dims, P, starts, 5)
+    s = BatchedSolver(dims, rb, cfg)
+    dev = lambda a: torch.as_tensor(a, dtype=torch.float64, device="cuda").contiguous()  # noqa: E731
+    o = {k: v.cpu().numpy() for k, v in s.run_batch(dev(P), dev(U0), starts=starts).items()}
+    _check_converged(dims, rb, P, o["u"], o["y"], o["penalty"], o["exit_status"], o["f2_norm"],
+                     starts=starts, want=8)
