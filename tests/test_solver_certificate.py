@@ -62,11 +62,11 @@ def test_gpu_converged_solutions_are_local_minimisers():
     from dyobav_mpcnwta_warehouse_b200.solver import BatchedSolver
     assert torch.cuda.is_available()
     dims, rb, cfg = Dims(), RobotSpec(), SolverSettings()
-    n_p, starts = 12, 4
+    n_p, starts = 24, 2      # 22 of these 48 solves converge
     P = instances.generate(dims, n_p, seed=5)
     U0 = instances.multistart_guesses(dims, P, starts, 5)
     s = BatchedSolver(dims, rb, cfg)
     dev = lambda a: torch.as_tensor(a, dtype=torch.float64, device="cuda").contiguous()  # noqa: E731
     o = {k: v.cpu().numpy() for k, v in s.run_batch(dev(P), dev(U0), starts=starts).items()}
     _check_converged(dims, rb, P, o["u"], o["y"], o["penalty"], o["exit_status"], o["f2_norm"],
-                     starts=starts, want=8)
+                     starts=starts, want=16)
