@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libmpcb.so")
 SOURCES = ["mpcb.cu"]
-HEADERS = ["mpcb_device.cuh", "mpcb_solver.cuh", os.path.join("..", "..", "include", "mpcb.h")]
+HEADERS = ["mpcb_device.cuh", "mpcb_solver.cuh", "mpcb_sim.cuh", os.path.join("..", "..", "include", "mpcb.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false",
               "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

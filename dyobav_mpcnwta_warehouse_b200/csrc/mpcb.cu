@@ -6,10 +6,12 @@
 //                     inverse squared radii, weights folded in: done once per
 //                     scenario instead of once per cost evaluation).
 //   K2 eval_kernel  : psi / grad psi / F1 / F2 for B instances (parity tests).
-//   K1 solve_kernel : persistent CTAs; each pulls a group of instances from an
-//                     atomic queue, TMA-bulk-loads the scenario block(s) into
-//                     shared memory, and every warp runs the whole ALM/PANOC
-//                     solve of one instance out of registers + shared memory.
+//   K1 solve_kernel_queue (default): persistent CTAs, one per SM, one work queue per CTA
+//                     (queue q owns scenarios q, q+grid, ...; idle warps steal); every warp
+//                     runs the whole ALM/PANOC solve of one instance out of registers and its
+//                     shared-memory scratch, reading the scenario block through L1.
+//      solve_kernel (MPCB_MODE=1, kept for comparison): CTA-synchronous groups that
+//                     TMA-bulk-load their scenario block(s) into shared memory.
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false
 // (-fmad=false: only the explicit fma() calls fuse, so the arithmetic does not
@@ -403,9 +405,10 @@ __global__ void __launch_bounds__(256) solve_kernel(const KParams P, const doubl
     }
 }
 
-// K1 (queue variant): every warp pulls its own next instance from the atomic queue, so a
-// slow instance never holds other warps at a CTA barrier; scenario blocks are read from the
-// staged copy in global memory (L1/L2-resident: with culling a solve touches a few KB of it).
+// K1 (queue variant): every warp pulls its own next instance (own CTA's queue first, then the
+// others': see solve_worker), so a slow instance never holds other warps at a CTA barrier;
+// scenario blocks are read from the staged copy in global memory through L1 (with culling a
+// solve touches a few KB of its block, and a CTA works on two or three blocks at a time).
 template <int SPL, int FIXED>
 __global__ void __launch_bounds__(qthreads(FIXED), MPCB_MIN_CTAS) solve_kernel_queue(const KParams P, const double* __restrict__ staged,
                                                           const SolveIO io, int* __restrict__ counter)
