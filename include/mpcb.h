@@ -114,7 +114,8 @@ void mpcb_default_solver_cfg(mpcb_solver_cfg* c);
 /*
  * Device workspace (bytes) the eval/solve entry points need for n_p parameter
  * rows: the staged structure-of-arrays copy of every row (K3 writes it, the
- * solve kernel TMA-loads it) plus the persistent work-queue counter.
+ * solve kernel reads it through L1 or TMA-loads it) plus a 4 KiB header holding
+ * the work-queue counters (one per persistent CTA).
  */
 int32_t mpcb_workspace_bytes(const mpcb_dims* dims, int32_t n_p, int32_t starts,
                              size_t* bytes);
