@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(256) eval_kernel(const KParams P, const double
     for (int j = 0; j < SPL; ++j) { ya[j] = ya[j] / fmax(cc, 1.0); yw[j] = yw[j] / fmax(cc, 1.0); }
     const int n2 = P.L.Ndyn > 0 ? P.L.Ndyn : 1;
     EvalOut<SPL> o;
-    eval_psi<SPL, 0>(P, S, v, w, cc, ya, yw, true, o, lane, F2 ? F2 + (size_t)b * n2 : nullptr);
+    eval_psi<SPL, 0>(P, S, v, w, cc, ya, yw, true, o, lane, F2 ? F2 + (size_t)b * n2 : nullptr, true);
     if (lane == 0) {
         if (f) f[b] = o.f;
         if (psi) psi[b] = o.psi;

@@ -413,7 +413,7 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
                                          const double (&v)[SPL], const double (&w)[SPL], double c,
                                          const double (&ya)[SPL], const double (&yw)[SPL],
                                          const bool GRAD, EvalOut<SPL>& out, int lane,
-                                         double* F2out = nullptr)
+                                         double* F2out = nullptr, const bool need_f = false)
 {
     const LayV<FIXED> L{&P.L};
     const int N = L.N();
@@ -796,11 +796,16 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
     }
 
     // ---- totals (butterfly: every lane ends with the same bits)
-    const double f = warp_sum(cost);
-    const double d2 = warp_sum(dist2);
-    out.f = f;
+    // ONE reduction per evaluation: every lane folds its share of the ALM distance term into its
+    // stage cost first, psi = sum_l (cost_l + c/2 dist2_l) + c/2 |F2|^2.  With c = 0 (the
+    // evaluation the ALM step makes to read f(u), F1, F2) the sum is f itself, bit for bit;
+    // a caller that wants f next to psi for c > 0 (the parity entry point K2) sets need_f and
+    // pays the second reduction.
+    const double hc = 0.5 * c;
+    const double ps = warp_sum(fma(hc, dist2, cost));
+    out.f = need_f ? warp_sum(cost) : ps;
     out.f2sq = f2sq;
-    out.psi = f + 0.5 * c * d2 + 0.5 * c * f2sq;
+    out.psi = fma(hc, f2sq, ps);
 
     if (GRAD) {
         // adjoint: G = sum_{j>=k} g_j ; theta coupling via a second suffix sum

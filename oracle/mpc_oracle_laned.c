@@ -541,11 +541,16 @@ static void eval_psi(const scen_t* S, lanes_t v, lanes_t w, double c, lanes_t ya
                 }
             }
     }
-    const double f = warp_sum(cost);
-    const double d2 = warp_sum(dist2);
-    out->f = f;
+    /* one reduction for psi, as the kernel does: each lane folds its share of the ALM distance
+       term into its stage cost before the butterfly; f is reduced separately (for c = 0 the
+       two sums have the same bits) */
+    const double hc = 0.5 * c;
+    double pl[W];
+    for (int l = 0; l < W; ++l) pl[l] = fma(hc, dist2[l], cost[l]);
+    const double ps = warp_sum(pl);
+    out->f = warp_sum(cost);
     out->f2sq = f2sq;
-    out->psi = f + 0.5 * c * d2 + 0.5 * c * f2sq;
+    out->psi = fma(hc, f2sq, ps);
     if (GRAD) {
         lanes_t Gx, Gy, hh, Hex;
         const double gthN_all = warp_sum(gthN);
