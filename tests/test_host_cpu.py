@@ -142,3 +142,20 @@ def test_hypotheses_to_obstacles_matches_numpy_fit():
         np.testing.assert_array_equal(od[c, 4, :2], np.mean(pts, axis=0))          # bit-exact vs numpy
         np.testing.assert_array_equal(od[c, 4, 2:4], np.std(pts, axis=0) * 2 + 0)
     assert (od[:, :, 5][(od[:, :, :4] != 0).any(-1)] == 1).all()
+
+
+@pytest.mark.parametrize("n_p,starts,nq", [(1, 1, 148), (301, 3, 148), (8192, 8, 148), (7, 5, 4), (148, 8, 148),
+                                           (149, 1, 148), (5, 8, 1)])
+def test_per_cta_queue_index_map_is_a_bijection(n_p, starts, nq):
+    """Host mirror of the index arithmetic of the solve kernel's work queues
+    (csrc/mpcb_solver.cuh, L_fetch): queue q owns scenarios q, q+nq, ...; ticket t of queue q is
+    start t % starts of that queue's (t // starts)-th scenario.  Every instance must be handed
+    out exactly once whatever the batch, the number of starts and the grid."""
+    seen = np.zeros(n_p * starts, dtype=np.int64)
+    for q in range(nq):
+        nsc_q = (n_p - q + nq - 1) // nq if q < n_p else 0
+        for t in range(nsc_q * starts):
+            sc = q + (t // starts) * nq
+            assert sc < n_p
+            seen[sc * starts + t % starts] += 1
+    assert (seen == 1).all()
