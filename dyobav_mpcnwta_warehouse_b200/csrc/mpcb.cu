@@ -103,6 +103,7 @@ __device__ __forceinline__ double hypot_plain(double a, double b) { return sqrt(
 __device__ __forceinline__ float margin_f(double dist, double R)
 {
     const double m = dist - R * (1.0 + 1e-9) - 1e-9;
+    if (m == INFINITY) return __int_as_float(0x7f800000);   // "never active" (zero-row polygon): INF - INF*1e-9 is NaN
     return __double2float_rd(m - fabs(m) * 1e-9);
 }
 
@@ -422,6 +423,90 @@ __global__ void __launch_bounds__(qthreads(FIXED), MPCB_MIN_CTAS) solve_kernel_q
     solve_worker<SPL, 1, FIXED>(P, nullptr, staged, counter, lb, 0, lane, io);
 }
 
+// K1 (team variant, dimension sets with many ellipses): one CTA per instance.  Warp 0 is the
+// solver (same code as the queue kernel, one queue per CTA), warps 1.. evaluate the ellipse cost
+// terms of every horizon evaluation (mpcb_device.cuh "team mode").
+template <int SPL, int FIXED>
+__global__ void __launch_bounds__(TEAM_THREADS, 1) solve_kernel_team(const KParams P, const double* __restrict__ staged,
+                                                                     const SolveIO io, int* __restrict__ counter)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* lb = reinterpret_cast<double*>(smem_raw);
+    TeamShared* T = reinterpret_cast<TeamShared*>(lb + P.lb_doubles);
+    int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) {
+        asm volatile("" : "+r"(lane));
+        solve_worker<SPL, 1, FIXED, true>(P, nullptr, staged, counter, lb, 0, lane, io, T);
+        if (lane == 0) T->cmd = 0;
+        __syncwarp();
+        bar_sync(1, TEAM_THREADS);
+    } else {
+        team_worker<FIXED>(P, T, (int)threadIdx.x - 32);
+    }
+}
+
+// K2 (team variant): one CTA per instance, same division of labour as solve_kernel_team
+template <int SPL>
+__global__ void __launch_bounds__(TEAM_THREADS, 1) eval_kernel_team(const KParams P, const double* __restrict__ staged,
+                                                                    const double* __restrict__ u,
+                                                                    const double* __restrict__ y,
+                                                                    const double* __restrict__ c, double* f,
+                                                                    double* psi, double* grad, double* F1, double* F2)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TeamShared* T = reinterpret_cast<TeamShared*>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp != 0) { team_worker<0>(P, T, (int)threadIdx.x - 32); return; }
+    const int N = P.L.N;
+    const int b = blockIdx.x;
+    const double* S = staged + (size_t)(b / P.starts) * P.L.total;
+    double v[SPL], w[SPL], ya[SPL], yw[SPL];
+    bool act[SPL];
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+        const int k = lane + 32 * j;
+        act[j] = k < N;
+        v[j] = 0.0; w[j] = 0.0; ya[j] = 0.0; yw[j] = 0.0;
+        if (act[j]) {
+            v[j] = u[(size_t)b * 2 * N + 2 * k];
+            w[j] = u[(size_t)b * 2 * N + 2 * k + 1];
+            if (y) { ya[j] = y[(size_t)b * 2 * N + k]; yw[j] = y[(size_t)b * 2 * N + N + k]; }
+        }
+    }
+    const double cc = c ? c[b] : P.c_init;
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) { ya[j] = ya[j] / fmax(cc, 1.0); yw[j] = yw[j] / fmax(cc, 1.0); }
+    const int n2 = P.L.Ndyn > 0 ? P.L.Ndyn : 1;
+    EvalOut<SPL> o;
+    eval_psi<SPL, 0, true>(P, S, v, w, cc, ya, yw, true, o, lane, F2 ? F2 + (size_t)b * n2 : nullptr, true, T);
+    if (lane == 0) T->cmd = 0;
+    __syncwarp();
+    bar_sync(1, TEAM_THREADS);
+    if (lane == 0) {
+        if (f) f[b] = o.f;
+        if (psi) psi[b] = o.psi;
+    }
+    double vc = S[P.L.o_hdr + H_UM1V], wc = S[P.L.o_hdr + H_UM1W];
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+        const int k = lane + 32 * j;
+        double vp = __shfl_up_sync(FULL, v[j], 1), wp = __shfl_up_sync(FULL, w[j], 1);
+        if (lane == 0) { vp = vc; wp = wc; }
+        if (SPL > 1) { vc = __shfl_sync(FULL, v[j], 31); wc = __shfl_sync(FULL, w[j], 31); }
+        if (act[j]) {
+            if (grad) {
+                grad[(size_t)b * 2 * N + 2 * k] = o.gv[j];
+                grad[(size_t)b * 2 * N + 2 * k + 1] = o.gw[j];
+            }
+            if (F1) {
+                F1[(size_t)b * 2 * N + k] = (v[j] - vp) * P.inv_ts;
+                F1[(size_t)b * 2 * N + N + k] = (w[j] - wp) * P.inv_ts;
+            }
+        }
+    }
+}
+
 // FP64 FMA throughput probe: the denominator of the roofline bench.py reports (the pool's
 // MEASURED_PEAKS.json has no FP64 figure).  8 independent DFMA chains per thread.
 __global__ void __launch_bounds__(256) fp64_peak_kernel(int iters, double seed, double* sink)
@@ -459,6 +544,7 @@ struct Plan {
     KParams P;
     bool smem;
     int fixed;     // compiled-in dimension set (0: run-time dims)
+    int team;      // worker groups of the team kernels (0: one-warp kernels)
     int spl;
     size_t smem_bytes;
 };
@@ -486,11 +572,13 @@ int make_plan(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solver_cfg* c,
     P.c_init = c->initial_penalty; P.sy_eps = c->sy_epsilon; P.cb_eps = c->cbfgs_epsilon;
     P.cb_alpha = c->cbfgs_alpha;
     P.max_inner = c->max_inner; P.max_outer = c->max_outer; P.mem = c->lbfgs_mem;
+    P.budget = c->max_inner_total > 0 ? c->max_inner_total : 0;
     P.n_p = n_p; P.starts = starts;
     const long long B = (long long)n_p * starts;
     if (B > 0x7fffffffLL / (2 * d->N)) return MPCB_E_DIMS;
     P.B = (int)B;
     pl.spl = d->N <= 32 ? 1 : 2;
+    pl.team = team_groups(d->N, d->Ndyn);
     const int M = c->lbfgs_mem + 1;
     // per-warp scratch: L-BFGS rows + rho/alpha, then y, y+ and the parked solver state
     P.lb_doubles = need_lbfgs ? (((2 * M * 2 * d->N + 2 * M + 1) & ~1) + scratch_doubles(d->N)) : 0;
@@ -535,6 +623,12 @@ int make_plan(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solver_cfg* c,
         while (P.warps > 1 && 16 + P.warps * lbw > cap) --P.warps;   // large N: fewer warps per CTA
         pl.smem_bytes = 16 + P.warps * lbw;
     }
+    if (pl.team) {
+        // one CTA per instance: warp 0's solver scratch, then the team scratch
+        pl.smem = false;
+        P.warps = MPCB_TEAM_WARPS; P.nsc = 0;
+        pl.smem_bytes = lbw + (size_t)team_doubles(d->N, pl.team) * 8;
+    }
     return MPCB_OK;
 }
 
@@ -578,6 +672,7 @@ int32_t mpcb_param_len(const mpcb_dims* d)
 int32_t mpcb_num_decision(const mpcb_dims* d) { return d ? 2 * d->N : -1; }
 int32_t mpcb_n1(const mpcb_dims* d) { return d ? 2 * d->N : -1; }
 int32_t mpcb_n2(const mpcb_dims* d) { return d ? (d->Ndyn > 0 ? d->Ndyn : 1) : -1; }
+int32_t mpcb_team_groups(const mpcb_dims* d) { return d ? team_groups(d->N, d->Ndyn) : -1; }
 
 void mpcb_default_robot(mpcb_robot* r)
 {
@@ -592,7 +687,7 @@ void mpcb_default_solver_cfg(mpcb_solver_cfg* c)
     c->tolerance = 1e-4; c->initial_tolerance = 1e-4; c->delta_tolerance = 1e-4;
     c->inner_tol_update = 0.1; c->penalty_update = 5.0; c->sufficient_decrease = 0.1;
     c->initial_penalty = 10.0; c->sy_epsilon = 1e-10; c->cbfgs_epsilon = 1e-8; c->cbfgs_alpha = 1.0;
-    c->max_inner = 500; c->max_outer = 10; c->lbfgs_mem = 10; c->reserved = 0;
+    c->max_inner = 500; c->max_outer = 10; c->lbfgs_mem = 10; c->max_inner_total = 0;
 }
 
 int32_t mpcb_workspace_bytes(const mpcb_dims* d, int32_t n_p, int32_t starts, size_t* bytes)
@@ -619,6 +714,19 @@ int32_t mpcb_eval_f64(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solver
     double* staged; int* counter;
     rc = stage(pl, p, workspace, ws_bytes, st, &staged, &counter);
     if (rc) return rc;
+    if (pl.team) {
+        if (pl.spl == 1) {
+            rc = set_smem(eval_kernel_team<1>, pl.smem_bytes);
+            if (rc) return rc;
+            eval_kernel_team<1><<<pl.P.B, TEAM_THREADS, pl.smem_bytes, st>>>(pl.P, staged, u, y, cpen, f, psi, grad, F1, F2);
+        } else {
+            rc = set_smem(eval_kernel_team<2>, pl.smem_bytes);
+            if (rc) return rc;
+            eval_kernel_team<2><<<pl.P.B, TEAM_THREADS, pl.smem_bytes, st>>>(pl.P, staged, u, y, cpen, f, psi, grad, F1, F2);
+        }
+        CUDA_TRY(cudaGetLastError());
+        return MPCB_OK;
+    }
     const int grid = (pl.P.B + pl.P.warps - 1) / pl.P.warps;
     const int threads = pl.P.warps * 32;
 #define LAUNCH_EVAL(SPL, SM)                                                                       \
@@ -684,19 +792,52 @@ int32_t mpcb_solve_f64(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solve
         if (grid > (int)(WS_HEADER / sizeof(int))) grid = (int)(WS_HEADER / sizeof(int));          \
         solve_kernel_queue<SPL, MD><<<grid, threads, pl.smem_bytes, st>>>(pl.P, staged, io, counter); \
     } while (0)
-    if (pl.smem) { if (pl.spl == 1) LAUNCH_SOLVE(1, true); else LAUNCH_SOLVE(2, true); }
+#define LAUNCH_TEAM(SPL, MD)                                                                       \
+    do {                                                                                           \
+        rc = set_smem(solve_kernel_team<SPL, MD>, pl.smem_bytes);                                  \
+        if (rc) return rc;                                                                         \
+        int per_sm = 0;                                                                            \
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_kernel_team<SPL, MD>, \
+                                                               TEAM_THREADS, pl.smem_bytes));      \
+        if (per_sm < 1) per_sm = 1;                                                                \
+        int grid = sms * per_sm;                                                                   \
+        if (grid > pl.P.B) grid = pl.P.B;                                                          \
+        if (grid > (int)(WS_HEADER / sizeof(int))) grid = (int)(WS_HEADER / sizeof(int));          \
+        solve_kernel_team<SPL, MD><<<grid, TEAM_THREADS, pl.smem_bytes, st>>>(pl.P, staged, io, counter); \
+    } while (0)
+    if (pl.team) {
+        if (pl.fixed == 3) LAUNCH_TEAM(2, 3);
+        else if (pl.spl == 1) LAUNCH_TEAM(1, 0);
+        else LAUNCH_TEAM(2, 0);
+    }
+    else if (pl.smem) { if (pl.spl == 1) LAUNCH_SOLVE(1, true); else LAUNCH_SOLVE(2, true); }
     else {
         if (pl.fixed == 1) LAUNCH_QUEUE(1, 1);
         else if (pl.fixed == 2) LAUNCH_QUEUE(1, 2);
-        else if (pl.fixed == 3) LAUNCH_QUEUE(2, 3);
         else if (pl.spl == 1) LAUNCH_QUEUE(1, 0);
         else LAUNCH_QUEUE(2, 0);
     }
 #undef LAUNCH_SOLVE
 #undef LAUNCH_QUEUE
+#undef LAUNCH_TEAM
     CUDA_TRY(cudaGetLastError());
     return MPCB_OK;
 }
+
+// Per-thread context of the single-solve host path: one device arena, one pinned staging buffer,
+// a private non-blocking stream and two events, all released when the thread ends.
+struct OneHostCtx {
+    char* dev = nullptr; char* pin = nullptr; size_t bytes = 0;
+    cudaStream_t st = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ~OneHostCtx()
+    {   // best effort: at process exit the CUDA context may already be gone
+        if (dev) cudaFree(dev);
+        if (pin) cudaFreeHost(pin);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        if (st) cudaStreamDestroy(st);
+    }
+};
 
 int32_t mpcb_solve_one_host(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solver_cfg* c,
                             const double* p_host, const double* u0_host, const double* y0_host,
@@ -715,32 +856,41 @@ int32_t mpcb_solve_one_host(const mpcb_dims* d, const mpcb_robot* r, const mpcb_
     const int n = 2 * d->N;
     size_t ws = 0;
     mpcb_workspace_bytes(d, 1, 1, &ws);
-    // one device arena: p | u0 | y0 | c0 | u | y | scalars(5 doubles) | ints(5) | workspace
-    const size_t o_p = 0, o_u0 = o_p + (size_t)L.np * 8, o_y0 = o_u0 + (size_t)n * 8,
-                 o_c0 = o_y0 + (size_t)n * 8, o_u = o_c0 + 16, o_y = o_u + (size_t)n * 8,
-                 o_sc = o_y + (size_t)n * 8, o_i = o_sc + 5 * 8, o_ws = (o_i + 5 * 4 + 255) & ~(size_t)255;
-    // per-thread cached device arena + events: the single-solve path is called once per
-    // control period, so allocation must not be on it
-    static thread_local char* t_arena = nullptr;
-    static thread_local size_t t_arena_bytes = 0;
-    static thread_local cudaEvent_t t_e0 = nullptr, t_e1 = nullptr;
-    if (t_arena_bytes < o_ws + ws) {
-        if (t_arena) cudaFree(t_arena);
-        t_arena = nullptr; t_arena_bytes = 0;
-        CUDA_TRY(cudaMalloc(&t_arena, o_ws + ws));
-        t_arena_bytes = o_ws + ws;
+    // one arena, mirrored on the device and in pinned host memory; every block starts on a
+    // 256-byte boundary (u0 / u_out feed double2 loads and stores: any np, odd ones included):
+    //   inputs  p | u0 | y0 | c0     outputs  u | y | scalars(5 doubles) | ints(5)     workspace
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t o_p = 0, o_u0 = up(o_p + (size_t)L.np * 8), o_y0 = up(o_u0 + (size_t)n * 8),
+                 o_c0 = up(o_y0 + (size_t)n * 8), o_in_end = up(o_c0 + 8);
+    const size_t o_u = o_in_end, o_y = up(o_u + (size_t)n * 8), o_sc = up(o_y + (size_t)n * 8),
+                 o_i = up(o_sc + 5 * 8), o_out_end = up(o_i + 5 * 4), o_ws = o_out_end;
+    // per-thread cached context: the single-solve path is called once per control period, so
+    // allocation must not be on it
+    static thread_local OneHostCtx t;
+    if (t.bytes < o_ws + ws) {
+        if (t.dev) cudaFree(t.dev);
+        if (t.pin) cudaFreeHost(t.pin);
+        t.dev = nullptr; t.pin = nullptr; t.bytes = 0;
+        CUDA_TRY(cudaMalloc(&t.dev, o_ws + ws));
+        CUDA_TRY(cudaMallocHost(&t.pin, o_out_end));
+        t.bytes = o_ws + ws;
     }
-    if (!t_e0) { CUDA_TRY(cudaEventCreate(&t_e0)); CUDA_TRY(cudaEventCreate(&t_e1)); }
-    char* arena = t_arena;
-    cudaStream_t st = 0;
-    cudaEvent_t e0 = t_e0, e1 = t_e1;
-    cudaMemcpyAsync(arena + o_p, p_host, (size_t)L.np * 8, cudaMemcpyHostToDevice, st);
-    if (u0_host) cudaMemcpyAsync(arena + o_u0, u0_host, (size_t)n * 8, cudaMemcpyHostToDevice, st);
-    if (y0_host) cudaMemcpyAsync(arena + o_y0, y0_host, (size_t)n * 8, cudaMemcpyHostToDevice, st);
-    if (c0_host) cudaMemcpyAsync(arena + o_c0, c0_host, 8, cudaMemcpyHostToDevice, st);
+    if (!t.st) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&t.st, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreate(&t.e0));
+        CUDA_TRY(cudaEventCreate(&t.e1));
+    }
+    char* arena = t.dev;
+    cudaStream_t st = t.st;
+    // stage the inputs in pinned memory: one asynchronous copy instead of pageable ones
+    memcpy(t.pin + o_p, p_host, (size_t)L.np * 8);
+    if (u0_host) memcpy(t.pin + o_u0, u0_host, (size_t)n * 8);
+    if (y0_host) memcpy(t.pin + o_y0, y0_host, (size_t)n * 8);
+    if (c0_host) memcpy(t.pin + o_c0, c0_host, 8);
+    CUDA_TRY(cudaMemcpyAsync(arena, t.pin, o_in_end, cudaMemcpyHostToDevice, st));
     double* sc = reinterpret_cast<double*>(arena + o_sc);
     int32_t* iv = reinterpret_cast<int32_t*>(arena + o_i);
-    cudaEventRecord(e0, st);
+    CUDA_TRY(cudaEventRecord(t.e0, st));
     rc = mpcb_solve_f64(d, r, c, 1, 1, reinterpret_cast<double*>(arena + o_p),
                         u0_host ? reinterpret_cast<double*>(arena + o_u0) : nullptr,
                         y0_host ? reinterpret_cast<double*>(arena + o_y0) : nullptr,
@@ -748,22 +898,20 @@ int32_t mpcb_solve_one_host(const mpcb_dims* d, const mpcb_robot* r, const mpcb_
                         reinterpret_cast<double*>(arena + o_u), sc + 0, iv + 0, iv + 1, iv + 2, sc + 1,
                         sc + 2, sc + 3, sc + 4, reinterpret_cast<double*>(arena + o_y), iv + 3,
                         arena + o_ws, ws, st);
-    cudaEventRecord(e1, st);
-    double hsc[5]; int32_t hiv[5];
-    if (rc == MPCB_OK) {
-        cudaMemcpyAsync(u_out_host, arena + o_u, (size_t)n * 8, cudaMemcpyDeviceToHost, st);
-        if (y_out_host) cudaMemcpyAsync(y_out_host, arena + o_y, (size_t)n * 8, cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(hsc, sc, sizeof(hsc), cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(hiv, iv, sizeof(hiv), cudaMemcpyDeviceToHost, st);
-    }
-    cudaError_t e = cudaStreamSynchronize(st);
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, e0, e1);
-    if (rc) return rc;
+    if (rc) { cudaStreamSynchronize(st); return rc; }
+    CUDA_TRY(cudaEventRecord(t.e1, st));
+    CUDA_TRY(cudaMemcpyAsync(t.pin + o_u, arena + o_u, o_out_end - o_u, cudaMemcpyDeviceToHost, st));
+    const cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) {
         snprintf(g_err, sizeof(g_err), "solve: %s", cudaGetErrorString(e));
         return MPCB_E_CUDA;
     }
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, t.e0, t.e1));
+    memcpy(u_out_host, t.pin + o_u, (size_t)n * 8);
+    if (y_out_host) memcpy(y_out_host, t.pin + o_y, (size_t)n * 8);
+    const double* hsc = reinterpret_cast<const double*>(t.pin + o_sc);
+    const int32_t* hiv = reinterpret_cast<const int32_t*>(t.pin + o_i);
     *exit_status_host = hiv[0];
     if (out_scalars) {
         out_scalars[0] = hsc[0]; out_scalars[1] = hsc[1]; out_scalars[2] = hsc[2];

@@ -74,6 +74,7 @@ struct KParams {
     int warps, nsc;      // warps per CTA, scenario blocks per CTA (shared-memory variant)
     int lb_doubles;      // per-warp L-BFGS scratch (doubles)
     int cull;            // 1: skip provably-zero obstacle terms
+    int budget;          // > 0: cap on the inner iterations of one solve (cfg->max_inner_total)
 };
 
 // One definition of the staged-block layout, usable at compile time (default dims are
@@ -151,6 +152,53 @@ struct LayV {
     MPCB_LAYF(total)
 #undef MPCB_LAYF
 };
+
+// ---------------------------------------------------------------- team mode
+// Dimension sets with many ellipses (Ndyn >= MPCB_TEAM_MIN_NDYN: the dense-crowd config, 160
+// ellipses x 40 steps) are solved by ONE CTA PER INSTANCE: warp 0 runs the solver exactly as the
+// one-warp kernel does, the other warps of the CTA ("workers") evaluate the ellipse cost terms of
+// every horizon evaluation in a flat (step, group) mapping - worker thread t owns step
+// k = t % N of group g = t / N and visits the candidate ellipses i with i % G == g - while warp 0
+// walks the reference path, the fleet and the polygons.  One instance per SM keeps the part of
+// its scenario block an evaluation touches resident in L1 (the one-warp kernel with 8 instances
+// per SM read it from DRAM every time: 22 stall cycles per issue on the long scoreboard).
+// ARITHMETIC CONTRACT of team mode (mirrored by the laned oracle): the ellipse cost terms of step
+// k are summed per group (in index order, from +0.0), and the G group sums are then added to the
+// step's stage cost / position gradient in group order; G = team_groups(N, Ndyn).  F2 (raw hinges)
+// keeps the one-warp order: workers only flag the ellipses that have a hinge, warp 0 redoes those.
+#ifndef MPCB_TEAM_WARPS
+#define MPCB_TEAM_WARPS 12
+#endif
+#ifndef MPCB_TEAM_MIN_NDYN
+#define MPCB_TEAM_MIN_NDYN 64
+#endif
+constexpr int TEAM_THREADS = 32 * MPCB_TEAM_WARPS;
+// number of worker groups (a power of two <= 32 with G*N <= worker threads); 0: one-warp kernel
+__host__ __device__ constexpr int team_groups(int N, int Ndyn)
+{
+    if (Ndyn < MPCB_TEAM_MIN_NDYN) return 0;
+    int g = 1;
+    while (2 * g <= 32 && 2 * g * N <= 32 * (MPCB_TEAM_WARPS - 1)) g *= 2;
+    return g;
+}
+struct TeamShared {
+    const double* S;       // scenario block of the instance being solved
+    int cmd;               // 1: evaluate, 0: exit
+    int grad;              // gradient wanted
+    unsigned cand[8];      // candidate ellipses of this evaluation (one bit each, Ndyn <= 256)
+    unsigned hit[8];       // ellipses with a raw hinge at some step (set by the workers)
+};
+static_assert(sizeof(TeamShared) == 80, "TeamShared is 10 doubles");
+// doubles of team scratch: header, X[N], Y[N], partial sums [3][G][N], D[N] (float)
+__host__ __device__ constexpr int team_doubles(int N, int G)
+{
+    return 10 + 2 * N + 3 * G * N + (N + 1) / 2;
+}
+__device__ __forceinline__ double* team_X(TeamShared* T) { return reinterpret_cast<double*>(T) + 10; }
+__device__ __forceinline__ void bar_sync(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 // ---------------------------------------------------------------- sin / cos
 // Cody-Waite reduction by pi/2 (two constants, exact first product for
@@ -408,12 +456,13 @@ struct EvalOut {
 #ifndef MPCB_EVAL_ATTR
 #define MPCB_EVAL_ATTR __forceinline__
 #endif
-template <int SPL, int FIXED>
+template <int SPL, int FIXED, bool TEAM = false>
 __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restrict__ S,
                                          const double (&v)[SPL], const double (&w)[SPL], double c,
                                          const double (&ya)[SPL], const double (&yw)[SPL],
                                          const bool GRAD, EvalOut<SPL>& out, int lane,
-                                         double* F2out = nullptr, const bool need_f = false)
+                                         double* F2out = nullptr, const bool need_f = false,
+                                         TeamShared* T = nullptr)
 {
     const LayV<FIXED> L{&P.L};
     const int N = L.N();
@@ -504,6 +553,26 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
 #pragma unroll
         for (int m = 16; m > 0; m >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(FULL, dmax, m));
         if (__any_sync(FULL, bad)) dmax = __int_as_float(0x7f800000);   // non-finite state: cull nothing
+    }
+    if constexpr (TEAM) {
+        // hand the positions and the candidate ellipses to the workers, then walk the path, the
+        // fleet and the polygons while they evaluate the ellipse cost terms
+        double* TX = team_X(T);
+        double* TY = TX + N;
+        float* TD = reinterpret_cast<float*>(TY + N + 3 * team_groups(N, L.Ndyn()) * N);
+        const float* ime = MG + L.f_imin();
+#pragma unroll
+        for (int j = 0; j < SPL; ++j)
+            if (act[j]) { TX[kk[j]] = X[j]; TY[kk[j]] = Y[j]; TD[kk[j]] = Df[j]; }
+#pragma unroll 1
+        for (int base = 0; base < L.Ndyn(); base += 32) {
+            const int it = base + lane;
+            const unsigned mk = __ballot_sync(FULL, it < L.Ndyn() && !(ime[it < L.Ndyn() ? it : 0] > dmax));
+            if (lane == 0) { T->cand[base >> 5] = mk; T->hit[base >> 5] = 0u; }
+        }
+        if (lane == 0) { T->S = S; T->grad = GRAD ? 1 : 0; T->cmd = 1; }
+        __syncwarp();
+        bar_sync(1, TEAM_THREADS);
     }
     const float* IM_E = MG + L.f_imin();
     const float* IM_P = IM_E + L.Ndyn();
@@ -653,6 +722,23 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
     //      gone.  F2's gradient terms go to their own accumulator (fx, fy), added to the cost
     //      gradient once at the end, so the order of the cost-gradient sum does not depend on
     //      which obstacles are hit.
+    if constexpr (TEAM) {
+        // the workers' group sums of the ellipse cost terms, added in group order
+        __syncwarp();
+        bar_sync(2, TEAM_THREADS);
+        const int G = team_groups(N, L.Ndyn());
+        const double* PC = team_X(T) + 2 * N;
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) {
+            if (act[j]) {
+#pragma unroll 1
+                for (int g = 0; g < G; ++g) {
+                    cstj[j] += PC[g * N + kk[j]];
+                    if (GRAD) { gx[j] += PC[(G + g) * N + kk[j]]; gy[j] += PC[(2 * G + g) * N + kk[j]]; }
+                }
+            }
+        }
+    }
     double f2sq = 0.0, sumF2 = 0.0;
     double fx[SPL], fy[SPL];
     bool anyF2;     // whether any entry of F2 can be non-zero or is wanted
@@ -671,7 +757,9 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
 #pragma unroll 1
         for (int base = 0; base < L.Ndyn(); base += 32) {
             const int it = base + lane;
-            unsigned mk = __ballot_sync(FULL, it < L.Ndyn() && !(IM_E[it < L.Ndyn() ? it : 0] > dmax));
+            // team mode: only the ellipses a worker flagged (a raw hinge somewhere) are redone here
+            unsigned mk = TEAM ? T->hit[base >> 5]
+                               : __ballot_sync(FULL, it < L.Ndyn() && !(IM_E[it < L.Ndyn() ? it : 0] > dmax));
             while (mk) {
                 const int i = base + __ffs(mk) - 1;
                 mk &= mk - 1;
@@ -683,13 +771,17 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
                     a[j].hr = 0.0; b[j].hr = 0.0;
                     if (!(me0b[i * N + k] > Df[j])) {          // t = 0 slot (one ellipse for all steps)
                         ellipse_terms(GRAD, e0 + i, L.Ndyn(), X[j], Y[j], a[j]);
-                        cstj[j] += a[j].cost;
-                        if (GRAD) { gx[j] += a[j].gx; gy[j] += a[j].gy; }
+                        if constexpr (!TEAM) {
+                            cstj[j] += a[j].cost;
+                            if (GRAD) { gx[j] += a[j].gx; gy[j] += a[j].gy; }
+                        }
                     }
                     if (!(metb[i * N + k] > Df[j])) {          // t = k+1 slot
                         ellipse_terms(GRAD, etb + k + i * N, L.Ndyn() * N, X[j], Y[j], b[j]);
-                        cstj[j] += b[j].cost;
-                        if (GRAD) { gx[j] += b[j].gx; gy[j] += b[j].gy; }
+                        if constexpr (!TEAM) {
+                            cstj[j] += b[j].cost;
+                            if (GRAD) { gx[j] += b[j].gx; gy[j] += b[j].gy; }
+                        }
                     }
                     if (!act[j]) { a[j].hr = 0.0; b[j].hr = 0.0; }
                     hl += a[j].hr + b[j].hr;
@@ -836,6 +928,69 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
             out.gv[j] = act[j] ? g0 : 0.0;
             out.gw[j] = act[j] ? g1 : 0.0;
         }
+    }
+}
+
+// Worker threads of a team (every warp of the CTA but warp 0); t = thread index among the workers.
+template <int FIXED>
+__device__ __forceinline__ void team_worker(const KParams& P, TeamShared* T, int t)
+{
+    const LayV<FIXED> L{&P.L};
+    const int N = L.N(), Ndyn = L.Ndyn();
+    const int G = team_groups(N, Ndyn);
+    const double* TX = team_X(T);
+    const double* TY = TX + N;
+    double* PC = team_X(T) + 2 * N;
+    const float* TD = reinterpret_cast<const float*>(PC + 3 * G * N);
+    const bool mine = t < G * N;
+    const int g = t / N, k = mine ? t - g * N : 0;
+    unsigned cls = 0u;                       // ellipses i with i % G == g (G divides 32)
+    for (int b = g; b < 32; b += G) cls |= 1u << b;
+    for (;;) {
+        bar_sync(1, TEAM_THREADS);
+        if (T->cmd == 0) return;
+        if (mine) {
+            const double* __restrict__ S = T->S;
+            const bool GRAD = T->grad != 0;
+            const float* MG = reinterpret_cast<const float*>(S + L.o_mg());
+            const float* me0b = MG + L.f_e0() + k;
+            const float* metb = MG + L.f_et() + k;
+            const double* e0 = S + L.o_e0();
+            const double* etb = S + L.o_et() + k;
+            const double x = TX[k], y = TY[k];
+            const float D = TD[k];
+            double pc = 0.0, pgx = 0.0, pgy = 0.0;
+#pragma unroll 1
+            for (int base = 0; base < Ndyn; base += 32) {
+                unsigned m = T->cand[base >> 5] & cls;
+                unsigned hits = 0u;
+#pragma unroll 1
+                while (m) {
+                    const int bit = __ffs(m) - 1;
+                    const int i = base + bit;
+                    m &= m - 1;
+                    EllT a, b;
+                    a.hr = 0.0; b.hr = 0.0;
+                    if (!(me0b[i * N] > D)) {              // t = 0 slot
+                        ellipse_terms(GRAD, e0 + i, Ndyn, x, y, a);
+                        pc += a.cost;
+                        if (GRAD) { pgx += a.gx; pgy += a.gy; }
+                    }
+                    if (!(metb[i * N] > D)) {              // t = k+1 slot
+                        ellipse_terms(GRAD, etb + i * N, Ndyn * N, x, y, b);
+                        pc += b.cost;
+                        if (GRAD) { pgx += b.gx; pgy += b.gy; }
+                    }
+                    if (a.hr > 0.0 || b.hr > 0.0) hits |= 1u << bit;
+                }
+                if (hits) atomicOr(&T->hit[base >> 5], hits);
+            }
+            PC[g * N + k] = pc;
+            PC[(G + g) * N + k] = pgx;
+            PC[(2 * G + g) * N + k] = pgy;
+        }
+        __syncwarp();
+        bar_sync(2, TEAM_THREADS);
     }
 }
 

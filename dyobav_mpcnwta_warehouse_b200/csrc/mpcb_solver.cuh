@@ -60,7 +60,9 @@ struct Inst {   // per-lane slice of the solver state of one instance
 };
 
 // Outer-loop (ALM) state of one instance: touched once per outer iteration, so it lives in the
-// warp's shared-memory scratch for good (every lane writes the same value: a benign broadcast).
+// warp's shared-memory scratch for good.  Every lane writes the same value; every read-modify-write
+// of a field is preceded by __syncwarp() (convergence + memory ordering), so no lane can read a value
+// another lane has already incremented.
 struct ColdState {
     double c;                      // penalty
     double akkt_tol;
@@ -221,10 +223,13 @@ enum EvalFor { ST_INIT, ST_INIT_LIP, ST_LIP_HALF, ST_LIP_U0, ST_LIP_LOOP, ST_NOL
 // AlmOptimizer::solve + PANOCOptimizer::solve + PANOCEngine::{init,step}.
 //   MODE 0: solve the one instance b0 whose scenario block is S0, then return.
 //   MODE 1: queue worker — pull instances from `counter` until the batch is exhausted.
-template <int SPL, int MODE, int FIXED>
+//   TEAM: this warp is warp 0 of a team (one CTA per instance): the other warps evaluate the
+//   ellipse cost terms of every horizon evaluation (mpcb_device.cuh "team mode").
+template <int SPL, int MODE, int FIXED, bool TEAM = false>
 __device__ __forceinline__ void solve_worker(const KParams& P, const double* __restrict__ S0,
                                              const double* __restrict__ staged, int* __restrict__ counter,
-                                             double* lb_mem, int b0, int lane, const SolveIO& io)
+                                             double* lb_mem, int b0, int lane, const SolveIO& io,
+                                             TeamShared* T = nullptr)
 {
     const LayV<FIXED> LV{&P.L};
     const int N = LV.N();
@@ -310,6 +315,10 @@ L_fetch:
     I.gamma = 0.0; I.sigma = 0.0; I.Lc = 0.0; I.cost = 0.0; I.norm_r = 0.0; I.iter = 0;
 
 L_outer_begin:   // ---- AlmOptimizer::step: project y on Y, then the inner problem
+    __syncwarp();
+    // AlmOptimizer::solve checks the remaining time before every outer iteration; here the clock
+    // is the inner-iteration count (cfg->max_inner_total, 0 = off)
+    if (P.budget > 0 && CS->inner_total >= P.budget) { CS->status = MPCB_NOT_CONVERGED_OUT_OF_TIME; goto L_finish; }
     CS->n_outer = CS->n_outer + 1;
     MPCB_FORJ {
         const int k = lane + 32 * j;
@@ -341,7 +350,8 @@ L_eval:
     reinterpret_cast<int*>(spark + 8)[2] = ls;
     reinterpret_cast<int*>(spark + 8)[3] = B.head;
     reinterpret_cast<int*>(spark + 8)[4] = B.active;
-    eval_psi<SPL, FIXED>(P, S, pt0, pt1, ceff, I.ya, I.yw, want_grad, o, lane);
+    eval_psi<SPL, FIXED, TEAM>(P, S, pt0, pt1, ceff, I.ya, I.yw, want_grad, o, lane, nullptr, false, T);
+    __syncwarp();   // reconverge after the divergent walks before the shared counters are touched
     // un-park (inactive lanes hold zeros in every vector)
     MPCB_FORJ {
         I.u0[j] = 0.0; I.u1[j] = 0.0; I.g0[j] = 0.0; I.g1[j] = 0.0;
@@ -511,7 +521,8 @@ H_LS: {
 L_step_return:   // PANOCOptimizer::solve: flag = step(); while (flag && cont) { ... step() }
     if (flag && cont) {
         ++num_iter;
-        cont = num_iter < P.max_inner;
+        // continue_num_iters && continue_runtime (the runtime being the iteration budget)
+        cont = num_iter < P.max_inner && (P.budget <= 0 || CS->inner_total + num_iter < P.budget);
         goto L_step_begin;
     }
     {
@@ -520,7 +531,9 @@ L_step_return:   // PANOCOptimizer::solve: flag = step(); while (flag && cont) {
         if (!__all_sync(FULL, fin)) { CS->status = MPCB_NOT_FINITE_COMPUTATION; CS->failed = 1; goto L_finish; }
     }
     MPCB_FORJ { I.u0[j] = I.h0[j]; I.u1[j] = I.h1[j]; }   // return u_bar (always feasible)
-    CS->inner = cont ? MPCB_CONVERGED : MPCB_NOT_CONVERGED_ITERATIONS;
+    __syncwarp();
+    CS->inner = cont ? MPCB_CONVERGED
+                     : (num_iter >= P.max_inner ? MPCB_NOT_CONVERGED_ITERATIONS : MPCB_NOT_CONVERGED_OUT_OF_TIME);
     CS->last_fpr = I.norm_r;
     CS->inner_total = CS->inner_total + num_iter;
     // F1(u), F2(u), f(u) at the inner solution: one horizon evaluation with c = 0
@@ -529,6 +542,7 @@ L_step_return:   // PANOCOptimizer::solve: flag = step(); while (flag && cont) {
     goto L_eval;
 
 H_ALM: {
+    __syncwarp();
     const double cpen = CS->c;
     const double fcost = o.f;
     const double f2n_plus = sqrt(o.f2sq);
@@ -597,6 +611,7 @@ L_finish:
         if (io.penalty) io.penalty[b] = CS->c;
         if (io.evals) { io.evals[2 * b] = CS->n_cost; io.evals[2 * b + 1] = CS->n_grad; }
     }
+    __syncwarp();   // lane 0's output block is done before the next instance resets the counters
     if (MODE != 0) goto L_fetch;
 }
 

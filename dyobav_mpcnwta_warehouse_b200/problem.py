@@ -50,7 +50,7 @@ class CSolverCfg(ctypes.Structure):
         "penalty_update", "sufficient_decrease", "initial_penalty", "sy_epsilon",
         "cbfgs_epsilon", "cbfgs_alpha")] + [
         ("max_inner", ctypes.c_int32), ("max_outer", ctypes.c_int32),
-        ("lbfgs_mem", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+        ("lbfgs_mem", ctypes.c_int32), ("max_inner_total", ctypes.c_int32)]
 
 
 @dataclass(frozen=True)
@@ -138,6 +138,9 @@ class SolverSettings:
     max_inner: int = 500
     max_outer: int = 10
     lbfgs_mem: int = 10
+    # 0 = off.  Budget on the inner iterations of one solve, the batch analogue of the reference's
+    # wall-clock cap ``max_solver_time`` (mpc_fast.yaml:45): exhausted -> "NotConvergedOutOfTime"
+    max_inner_total: int = 0
 
     def __post_init__(self):
         if not (1 <= self.lbfgs_mem <= MAX_LBFGS):
@@ -148,7 +151,7 @@ class SolverSettings:
                           self.inner_tol_update, self.penalty_update,
                           self.sufficient_decrease, self.initial_penalty, self.sy_epsilon,
                           self.cbfgs_epsilon, self.cbfgs_alpha, self.max_inner,
-                          self.max_outer, self.lbfgs_mem, 0)
+                          self.max_outer, self.lbfgs_mem, int(self.max_inner_total))
 
 
 # The yaml keys of config/mpc_fast.yaml / mpc_default.yaml with their shipped

@@ -41,7 +41,7 @@ extern "C" {
  *      config/mpc_fast.yaml:48 `bad_exit_codes` refers to) ------------------- */
 #define MPCB_CONVERGED                   0
 #define MPCB_NOT_CONVERGED_ITERATIONS    1
-#define MPCB_NOT_CONVERGED_OUT_OF_TIME   2  /* never produced: no wall clock on a batch */
+#define MPCB_NOT_CONVERGED_OUT_OF_TIME   2  /* only with cfg->max_inner_total > 0 (iteration budget) */
 #define MPCB_NOT_FINITE_COMPUTATION      3
 
 /*
@@ -89,7 +89,14 @@ typedef struct mpcb_solver_cfg {
     int32_t max_inner;           /* 500                                         */
     int32_t max_outer;           /* 10                                          */
     int32_t lbfgs_mem;           /* 10 (<= MPCB_MAX_LBFGS)                      */
-    int32_t reserved;
+    int32_t max_inner_total;     /* 0 = off.  Budget on the inner (PANOC) iterations of ONE solve,
+                                  * summed over the outer iterations: the batch analogue of the
+                                  * reference's wall-clock cap max_solver_time (mpc_fast.yaml:45,
+                                  * mpc_builder.py:189).  The clock is the iteration count: the inner
+                                  * loop stops when the budget is used up (inner status
+                                  * NotConvergedOutOfTime), the ALM step finishes as usual and the
+                                  * next outer iteration is refused with MPCB_NOT_CONVERGED_OUT_OF_TIME,
+                                  * the status mpc_fast.yaml:48 lists in bad_exit_codes.             */
 } mpcb_solver_cfg;
 
 #define MPCB_MAX_LBFGS 10
@@ -103,6 +110,11 @@ int32_t mpcb_param_len(const mpcb_dims* dims);
 int32_t mpcb_num_decision(const mpcb_dims* dims);
 int32_t mpcb_n1(const mpcb_dims* dims);
 int32_t mpcb_n2(const mpcb_dims* dims);
+
+/* Worker groups G of the team kernels for these dims (0: the one-warp kernels are used).  Part of
+ * the arithmetic contract: with G > 0 the ellipse cost terms of a horizon step are summed per
+ * group i % G first (csrc/mpcb_device.cuh "team mode"); the laned oracle mirrors the rule. */
+int32_t mpcb_team_groups(const mpcb_dims* dims);
 
 int32_t mpcb_abi_version(void);
 /* Text of the last CUDA error seen by this thread ("" if none). */

@@ -768,20 +768,24 @@ static int panoc_step(panoc_t* S, double* u)
 }
 
 /* PANOCOptimizer::solve ; returns inner exit status, iterations in *iters */
-static int panoc_solve(panoc_t* S, double* u, int* iters)
+static int panoc_solve(panoc_t* S, double* u, int* iters, int iters_left /* <= 0: no budget */)
 {
     panoc_init(S, u);
-    int num_iter = 0, cont = 1;
+    int num_iter = 0, cont_it = 1, cont_rt = 1;
     int flag = panoc_step(S, u);
-    while (flag && cont) {
+    while (flag && cont_it && cont_rt) {
         num_iter++;
-        cont = num_iter < S->cfg->max_inner;
+        cont_it = num_iter < S->cfg->max_inner;
+        /* continue_runtime: the reference's wall clock (max_solver_time) restated as a budget on
+         * the inner iterations of the whole solve (cfg->max_inner_total) */
+        cont_rt = iters_left <= 0 || num_iter < iters_left;
         flag = panoc_step(S, u);
     }
     *iters = num_iter;
     for (int i = 0; i < S->n; ++i)
         if (!isfinite(u[i])) return MPCB_NOT_FINITE_COMPUTATION;
-    int status = cont ? MPCB_CONVERGED : MPCB_NOT_CONVERGED_ITERATIONS;
+    int status = !cont_it ? MPCB_NOT_CONVERGED_ITERATIONS
+                          : (!cont_rt ? MPCB_NOT_CONVERGED_OUT_OF_TIME : MPCB_CONVERGED);
     memcpy(u, S->u_half, sizeof(double) * (size_t)S->n);
     return status;
 }
@@ -820,7 +824,13 @@ int32_t mpco_solve(const mpcb_dims* d, const mpcb_robot* rb, const mpcb_solver_c
     int exit_status = MPCB_CONVERGED;
     int failed = 0;
 
+    const int budget = cfg->max_inner_total > 0 ? cfg->max_inner_total : 0;
     for (int outer = 1; outer <= cfg->max_outer; ++outer) {
+        /* AlmOptimizer::solve: "no time left" before an outer iteration -> NotConvergedOutOfTime */
+        if (budget > 0 && inner_total >= budget) {
+            exit_status = MPCB_NOT_CONVERGED_OUT_OF_TIME;
+            break;
+        }
         n_outer++;
         /* project y on Y = [-1e12,1e12]^n1 */
         for (int i = 0; i < n1; ++i)
@@ -828,7 +838,7 @@ int32_t mpco_solve(const mpcb_dims* d, const mpcb_robot* rb, const mpcb_solver_c
         /* set_akkt_tolerance zeroes the cached previous gradient */
         memset(S->grad_prev, 0, sizeof(S->grad_prev));
         int iters = 0;
-        int inner_status = panoc_solve(S, u, &iters);
+        int inner_status = panoc_solve(S, u, &iters, budget > 0 ? budget - inner_total : 0);
         if (inner_status == MPCB_NOT_FINITE_COMPUTATION) {
             exit_status = MPCB_NOT_FINITE_COMPUTATION;
             failed = 1;

@@ -33,6 +33,7 @@ typedef double lanes_t[JMAX][W];
 
 typedef struct {
     int N, J, Nother, Nstc, nedge, Ndyn;
+    int G;                     /* worker groups of team mode (0: one-warp order) */
     double ts, k6, inv_ts, ds2, vmargin, smargin;
     double vmin, vmax, wmax, amin, amax, wamax;
     /* staged scenario */
@@ -156,6 +157,19 @@ static double dotw(int J, lanes_t a0, lanes_t a1, lanes_t b0, lanes_t b1)
     return warp_sum(p);
 }
 
+/* Team mode (arithmetic contract, csrc/mpcb_device.cuh "team mode"): dimension sets with at
+ * least 64 ellipses are solved by a 12-warp CTA per instance whose 11 worker warps own
+ * (step, group) pairs; the number of groups is the largest power of two G <= 32 with
+ * G*N <= 352.  The ellipse cost terms of a step are summed per group i % G (index order, from
+ * +0.0) and the group sums are added to the step's stage cost / gradient in group order. */
+int32_t mpcl_team_groups(const mpcb_dims* d)
+{
+    if (d->Ndyn < 64) return 0;
+    int g = 1;
+    while (2 * g <= 32 && 2 * g * d->N <= 32 * 11) g *= 2;
+    return g;
+}
+
 /* ---- staging (K3): raw parameter row -> scenario ---- */
 static void scen_free(scen_t* S)
 {
@@ -168,6 +182,7 @@ static int scen_stage(scen_t* S, const mpcb_dims* d, const mpcb_robot* rb, const
     if (N < 1 || N > MAXN || d->nedge < 1 || d->nedge > MPCB_MAX_EDGE) return MPCB_E_DIMS;
     S->N = N; S->J = N <= W ? 1 : 2;
     S->Nother = d->Nother; S->Nstc = d->Nstc; S->nedge = d->nedge; S->Ndyn = d->Ndyn;
+    S->G = mpcl_team_groups(d);
     S->ts = rb->ts; S->k6 = rb->ts / 6.0; S->inv_ts = 1.0 / rb->ts;
     S->ds2 = rb->vehicle_width * rb->vehicle_width;
     S->vmargin = rb->vehicle_margin; S->smargin = rb->social_margin;
@@ -421,14 +436,33 @@ static void eval_psi(const scen_t* S, lanes_t v, lanes_t w, double c, lanes_t ya
                     }
                 }
             }
-            for (int i = 0; i < S->Ndyn; ++i) {   /* dynamic ellipses */
-                ell_t a, b;
-                ellipse_terms(GRAD, S->e0 + i, S->Ndyn, x, y, &a);
-                cst += a.cost;
-                if (GRAD) { ggx += a.gx; ggy += a.gy; }
-                ellipse_terms(GRAD, S->et + k + i * N, S->Ndyn * N, x, y, &b);
-                cst += b.cost;
-                if (GRAD) { ggx += b.gx; ggy += b.gy; }
+            if (S->G == 0) {
+                for (int i = 0; i < S->Ndyn; ++i) {   /* dynamic ellipses */
+                    ell_t a, b;
+                    ellipse_terms(GRAD, S->e0 + i, S->Ndyn, x, y, &a);
+                    cst += a.cost;
+                    if (GRAD) { ggx += a.gx; ggy += a.gy; }
+                    ellipse_terms(GRAD, S->et + k + i * N, S->Ndyn * N, x, y, &b);
+                    cst += b.cost;
+                    if (GRAD) { ggx += b.gx; ggy += b.gy; }
+                }
+            } else {                                  /* team mode: per-group sums first */
+                double pc[32], pgx[32], pgy[32];
+                for (int g = 0; g < S->G; ++g) { pc[g] = 0.0; pgx[g] = 0.0; pgy[g] = 0.0; }
+                for (int i = 0; i < S->Ndyn; ++i) {
+                    const int g = i % S->G;
+                    ell_t a, b;
+                    ellipse_terms(GRAD, S->e0 + i, S->Ndyn, x, y, &a);
+                    pc[g] += a.cost;
+                    if (GRAD) { pgx[g] += a.gx; pgy[g] += a.gy; }
+                    ellipse_terms(GRAD, S->et + k + i * N, S->Ndyn * N, x, y, &b);
+                    pc[g] += b.cost;
+                    if (GRAD) { pgx[g] += b.gx; pgy[g] += b.gy; }
+                }
+                for (int g = 0; g < S->G; ++g) {
+                    cst += pc[g];
+                    if (GRAD) { ggx += pgx[g]; ggy += pgy[g]; }
+                }
             }
             if (!act[j][l]) { cst = 0.0; ggx = 0.0; ggy = 0.0; sp = 0.0; spx = 0.0; spy = 0.0; gvd[j][l] = 0.0; gwd[j][l] = 0.0; }
             cost[l] += cst;
@@ -885,7 +919,11 @@ int32_t mpcl_solve(const mpcb_dims* d, const mpcb_robot* rb, const mpcb_solver_c
     const double EPS = 2.220446049250313e-16;
     eval_out_t o;
 
+    const int budget = cfg->max_inner_total > 0 ? cfg->max_inner_total : 0;
     for (int outer = 1; outer <= cfg->max_outer; ++outer) {
+        /* AlmOptimizer::solve: no time left -> NotConvergedOutOfTime (the clock is the inner
+           iteration count, cfg->max_inner_total) */
+        if (budget > 0 && inner_total >= budget) { status = MPCB_NOT_CONVERGED_OUT_OF_TIME; break; }
         ++n_outer;
         FORJL {
             I->ya[j][l] = fmin(fmax(I->ya[j][l], -1e12), 1e12);
@@ -925,14 +963,16 @@ int32_t mpcl_solve(const mpcb_dims* d, const mpcb_robot* rb, const mpcb_solver_c
         int flag = panoc_step(cfg, S, I, B);
         while (flag && cont) {
             ++num_iter;
-            cont = num_iter < cfg->max_inner;
+            cont = num_iter < cfg->max_inner && (budget <= 0 || inner_total + num_iter < budget);
             flag = panoc_step(cfg, S, I, B);
         }
         int fin = 1;
         FORJL fin = fin && isfinite(I->u0[j][l]) && isfinite(I->u1[j][l]);
         if (!fin) { status = MPCB_NOT_FINITE_COMPUTATION; failed = 1; break; }
         FORJL { I->u0[j][l] = I->h0[j][l]; I->u1[j][l] = I->h1[j][l]; }
-        const int inner = cont ? MPCB_CONVERGED : MPCB_NOT_CONVERGED_ITERATIONS;
+        const int inner = cont ? MPCB_CONVERGED
+                               : (num_iter >= cfg->max_inner ? MPCB_NOT_CONVERGED_ITERATIONS
+                                                             : MPCB_NOT_CONVERGED_OUT_OF_TIME);
         last_fpr = I->norm_r;
         inner_total += num_iter;
         eval_at(S, I, I->u0, I->u1, 0.0, 0, &o);

@@ -35,6 +35,7 @@ def lib():
         L.mpcl_eval.restype = ctypes.c_int32
         L.mpcl_solve.restype = ctypes.c_int32
         L.mpcl_solve_batch.restype = ctypes.c_int32
+        L.mpcl_team_groups.restype = ctypes.c_int32
         for f in (L.mpco_dist_to_lineseg, L.mpco_inside_ellipse, L.mpco_inside_cvx_polygon):
             f.restype = ctypes.c_double
         L.mpco_dist_to_lineseg.argtypes = [ctypes.c_double] * 6

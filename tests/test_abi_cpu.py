@@ -59,6 +59,22 @@ def test_argument_errors_are_codes_not_crashes(cuda_solver_lib):
     assert L.mpcb_solve_f64(*args) == -2
 
 
+def test_team_rule_is_the_same_in_library_and_oracle(cuda_solver_lib):
+    """Team mode changes the summation order of the ellipse cost terms: the laned oracle must use
+    the same number of worker groups as the kernels for every dimension set."""
+    from oracle import oracle
+    OL = oracle.lib()
+    for N in (1, 7, 11, 12, 20, 32, 33, 40, 64):
+        for Ndyn in (0, 15, 40, 63, 64, 70, 160, 256):
+            cd = Dims(N=N, Ndyn=Ndyn).to_c()
+            g = cuda_solver_lib.mpcb_team_groups(ctypes.byref(cd))
+            assert g == OL.mpcl_team_groups(ctypes.byref(cd)), (N, Ndyn)
+            assert g == 0 or (g & (g - 1) == 0 and g <= 32 and g * N <= 352), (N, Ndyn, g)
+    assert cuda_solver_lib.mpcb_team_groups(ctypes.byref(Dims().to_c())) == 0
+    assert cuda_solver_lib.mpcb_team_groups(ctypes.byref(Dims(Ndyn=40).to_c())) == 0
+    assert cuda_solver_lib.mpcb_team_groups(ctypes.byref(Dims(N=40, Ndyn=160).to_c())) == 8
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "_lib", None)
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
