@@ -199,6 +199,30 @@ __global__ void __launch_bounds__(128) stage_kernel(const KParams P, const doubl
                 MG[L.f_et + i] = margin_f(hypot_plain(q[0] - ax, q[1] - ay), Rb);
             }
         }
+        // bounding boxes of the inflated ellipses, per obstacle (t = 0 slot) and per obstacle and
+        // block of 8 steps (t = k+1 slots): the position-based culling test of the team kernels
+        // (a robot that lags behind its reference makes every anchor-based margin useless)
+        {
+            const int NB = (N + 7) / 8;
+            for (int idx = tid; idx < L.Ndyn * (NB + 1); idx += nt) {
+                const int ob = idx / (NB + 1), b = idx - ob * (NB + 1) - 1;     // b = -1: the t = 0 slot
+                const int k0 = b < 0 ? -1 : 8 * b, k1 = b < 0 ? 0 : (8 * b + 8 < N ? 8 * b + 8 : N);
+                float x0 = __int_as_float(0x7f800000), x1 = -x0, y0 = x0, y1 = -x0;
+                bool bad = false;
+                for (int k = k0; k < k1; ++k) {
+                    const double* q = pr + L.p_od + (size_t)(ob * (N + 1) + k + 1) * 6;
+                    const double infl = b < 0 ? P.vmargin + P.smargin : P.vmargin;
+                    const double Rb = fmax(fabs(q[2] + infl + 1e-6), fabs(q[3] + infl + 1e-6)) * (1.0 + 1e-9) + 1e-9;
+                    const double lx = q[0] - Rb, hx = q[0] + Rb, ly = q[1] - Rb, hy = q[1] + Rb;
+                    bad |= !(lx == lx) || !(hx == hx) || !(ly == ly) || !(hy == hy);
+                    x0 = fminf(x0, __double2float_rd(lx - fabs(lx) * 1e-9)); x1 = fmaxf(x1, __double2float_ru(hx + fabs(hx) * 1e-9));
+                    y0 = fminf(y0, __double2float_rd(ly - fabs(ly) * 1e-9)); y1 = fmaxf(y1, __double2float_ru(hy + fabs(hy) * 1e-9));
+                }
+                if (bad) { x0 = x1 = y0 = y1 = __int_as_float(0x7fc00000); }   // NaN: never culled
+                float* o = b < 0 ? MG + L.f_bx0 + 4 * ob : MG + L.f_bx1 + 4 * (ob * NB + b);
+                o[0] = x0; o[1] = x1; o[2] = y0; o[3] = y1;
+            }
+        }
         for (int i = tid; i < L.Nother * N; i += nt) {         // i = r*N + k
             const int r = i / N, k = i - r * N;
             const double ax = sg[k], ay = sg[N + k];
@@ -423,30 +447,37 @@ __global__ void __launch_bounds__(qthreads(FIXED), MPCB_MIN_CTAS) solve_kernel_q
     solve_worker<SPL, 1, FIXED>(P, nullptr, staged, counter, lb, 0, lane, io);
 }
 
-// K1 (team variant, dimension sets with many ellipses): one CTA per instance.  Warp 0 is the
-// solver (same code as the queue kernel, one queue per CTA), warps 1.. evaluate the ellipse cost
-// terms of every horizon evaluation (mpcb_device.cuh "team mode").
+// K1 (team variant, dimension sets with many ellipses): TEAM_NS solver warps per CTA, each running
+// the solve of one instance (same code as the queue kernel, one queue per CTA), share the worker
+// warps, which evaluate the per-step part of every horizon evaluation (mpcb_device.cuh "team mode").
 template <int SPL, int FIXED>
-__global__ void __launch_bounds__(TEAM_THREADS, 1) solve_kernel_team(const KParams P, const double* __restrict__ staged,
+__global__ void __launch_bounds__(TEAM_THREADS, MPCB_TEAM_CTAS) solve_kernel_team(const KParams P, const double* __restrict__ staged,
                                                                      const SolveIO io, int* __restrict__ counter)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* lb = reinterpret_cast<double*>(smem_raw);
-    TeamShared* T = reinterpret_cast<TeamShared*>(lb + P.lb_doubles);
+    double* base = reinterpret_cast<double*>(smem_raw);
+    const int sstride = P.lb_doubles + team_solver_doubles(P.L.N);
+    TeamPool* pool = reinterpret_cast<TeamPool*>(base + (size_t)TEAM_NS * sstride);
     int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    if (warp == 0) {
+    if (threadIdx.x < TEAM_NS) {
+        TeamShared* Ts = reinterpret_cast<TeamShared*>(base + (size_t)threadIdx.x * sstride + P.lb_doubles);
+        Ts->req = 0; Ts->done = 0; Ts->exit_ = 0;
+    }
+    __syncthreads();
+    if (warp < TEAM_NS) {
+        double* lb = base + (size_t)warp * sstride;
+        TeamShared* T = reinterpret_cast<TeamShared*>(lb + P.lb_doubles);
         asm volatile("" : "+r"(lane));
         solve_worker<SPL, 1, FIXED, true>(P, nullptr, staged, counter, lb, 0, lane, io, T);
-        if (lane == 0) T->cmd = 0;
         __syncwarp();
-        bar_sync(1, TEAM_THREADS);
+        if (lane == 0) { __threadfence_block(); T->exit_ = 1; }
     } else {
-        team_worker<FIXED>(P, T, (int)threadIdx.x - 32);
+        team_worker<FIXED>(P, base, sstride, P.lb_doubles, TEAM_NS, pool, (int)threadIdx.x - 32 * TEAM_NS);
     }
 }
 
-// K2 (team variant): one CTA per instance, same division of labour as solve_kernel_team
+// K2 (team variant): one CTA per instance, warp 0 evaluates, same division of labour
 template <int SPL>
 __global__ void __launch_bounds__(TEAM_THREADS, 1) eval_kernel_team(const KParams P, const double* __restrict__ staged,
                                                                     const double* __restrict__ u,
@@ -455,10 +486,15 @@ __global__ void __launch_bounds__(TEAM_THREADS, 1) eval_kernel_team(const KParam
                                                                     double* psi, double* grad, double* F1, double* F2)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    TeamShared* T = reinterpret_cast<TeamShared*>(smem_raw);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (warp != 0) { team_worker<0>(P, T, (int)threadIdx.x - 32); return; }
+    double* base = reinterpret_cast<double*>(smem_raw);
+    TeamShared* T = reinterpret_cast<TeamShared*>(base);
     const int N = P.L.N;
+    TeamPool* pool = reinterpret_cast<TeamPool*>(base + team_solver_doubles(N));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { T->req = 0; T->done = 0; T->exit_ = 0; }
+    __syncthreads();
+    if (warp >= TEAM_NS) { team_worker<0>(P, base, team_solver_doubles(N), 0, 1, pool, (int)threadIdx.x - 32 * TEAM_NS); return; }
+    if (warp != 0) return;
     const int b = blockIdx.x;
     const double* S = staged + (size_t)(b / P.starts) * P.L.total;
     double v[SPL], w[SPL], ya[SPL], yw[SPL];
@@ -480,9 +516,8 @@ __global__ void __launch_bounds__(TEAM_THREADS, 1) eval_kernel_team(const KParam
     const int n2 = P.L.Ndyn > 0 ? P.L.Ndyn : 1;
     EvalOut<SPL> o;
     eval_psi<SPL, 0, true>(P, S, v, w, cc, ya, yw, true, o, lane, F2 ? F2 + (size_t)b * n2 : nullptr, true, T);
-    if (lane == 0) T->cmd = 0;
     __syncwarp();
-    bar_sync(1, TEAM_THREADS);
+    if (lane == 0) { __threadfence_block(); T->exit_ = 1; }
     if (lane == 0) {
         if (f) f[b] = o.f;
         if (psi) psi[b] = o.psi;
@@ -624,10 +659,11 @@ int make_plan(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solver_cfg* c,
         pl.smem_bytes = 16 + P.warps * lbw;
     }
     if (pl.team) {
-        // one CTA per instance: warp 0's solver scratch, then the team scratch
+        // per solver warp its scratch and its team block, then the worker pool's scratch; the
+        // evaluation kernel has one solver and no solver scratch
         pl.smem = false;
         P.warps = MPCB_TEAM_WARPS; P.nsc = 0;
-        pl.smem_bytes = lbw + (size_t)team_doubles(d->N, pl.team) * 8;
+        pl.smem_bytes = (size_t)team_smem_doubles(d->N, pl.team, P.lb_doubles, need_lbfgs ? TEAM_NS : 1) * 8;
     }
     return MPCB_OK;
 }
@@ -801,7 +837,7 @@ int32_t mpcb_solve_f64(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solve
                                                                TEAM_THREADS, pl.smem_bytes));      \
         if (per_sm < 1) per_sm = 1;                                                                \
         int grid = sms * per_sm;                                                                   \
-        if (grid > pl.P.B) grid = pl.P.B;                                                          \
+        if (grid > (pl.P.B + TEAM_NS - 1) / TEAM_NS) grid = (pl.P.B + TEAM_NS - 1) / TEAM_NS;       \
         if (grid > (int)(WS_HEADER / sizeof(int))) grid = (int)(WS_HEADER / sizeof(int));          \
         solve_kernel_team<SPL, MD><<<grid, TEAM_THREADS, pl.smem_bytes, st>>>(pl.P, staged, io, counter); \
     } while (0)
@@ -827,7 +863,7 @@ int32_t mpcb_solve_f64(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solve
 // Per-thread context of the single-solve host path: one device arena, one pinned staging buffer,
 // a private non-blocking stream and two events, all released when the thread ends.
 struct OneHostCtx {
-    char* dev = nullptr; char* pin = nullptr; size_t bytes = 0;
+    char* dev = nullptr; char* pin = nullptr; size_t bytes = 0, pin_bytes = 0;
     cudaStream_t st = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
     ~OneHostCtx()
     {   // best effort: at process exit the CUDA context may already be gone
@@ -869,11 +905,15 @@ int32_t mpcb_solve_one_host(const mpcb_dims* d, const mpcb_robot* r, const mpcb_
     static thread_local OneHostCtx t;
     if (t.bytes < o_ws + ws) {
         if (t.dev) cudaFree(t.dev);
-        if (t.pin) cudaFreeHost(t.pin);
-        t.dev = nullptr; t.pin = nullptr; t.bytes = 0;
+        t.dev = nullptr; t.bytes = 0;
         CUDA_TRY(cudaMalloc(&t.dev, o_ws + ws));
-        CUDA_TRY(cudaMallocHost(&t.pin, o_out_end));
         t.bytes = o_ws + ws;
+    }
+    if (t.pin_bytes < o_out_end) {
+        if (t.pin) cudaFreeHost(t.pin);
+        t.pin = nullptr; t.pin_bytes = 0;
+        CUDA_TRY(cudaMallocHost(&t.pin, o_out_end));
+        t.pin_bytes = o_out_end;
     }
     if (!t.st) {
         CUDA_TRY(cudaStreamCreateWithFlags(&t.st, cudaStreamNonBlocking));

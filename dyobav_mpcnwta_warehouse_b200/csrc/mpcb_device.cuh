@@ -58,6 +58,9 @@ struct Lay {            // offsets (in doubles) inside one staged scenario block
     int f_seg;          // [N][N]: (k, i) -> min over segments i' >= i of dist(A_k, segment i')
     int f_seg2;         // [N][N]: (k, i) -> min over segments i' >= i of (x - A_k).t_k, x on the segment,
                         // t_k the (slightly shortened) unit tangent of segment k: a directional bound
+    int f_bx0;          // [Ndyn][4]: bounding box (xmin, xmax, ymin, ymax) of the inflated t = 0 ellipse
+    int f_bx1;          // [Ndyn][NB][4]: bounding box of the inflated t = k+1 ellipses of the steps of block b
+                        // (blocks of 8 steps, NB = ceil(N/8)); both 16-byte aligned, rounded outwards
     int total;          // doubles, multiple of 2 (16-byte granularity for TMA bulk copies)
     int np;             // length of a raw parameter row
     // raw p offsets (mpc_builder.py:47-60)
@@ -103,6 +106,9 @@ __host__ __device__ constexpr Lay make_lay(int N, int Nother, int Nstc, int nedg
     L.f_imin = fo; fo += Ndyn + Nstc + 2 * Nother;
     L.f_seg = fo;  fo += N * N;
     L.f_seg2 = fo; fo += N * N;
+    while ((2 * L.o_mg + fo) & 3) ++fo;          // float4 loads
+    L.f_bx0 = fo;  fo += 4 * Ndyn;
+    L.f_bx1 = fo;  fo += 4 * Ndyn * ((N + 7) / 8);
     o += (fo + 1) / 2;
     L.total = (o + 1) & ~1;
     int q = 0;
@@ -148,53 +154,109 @@ struct LayV {
     MPCB_LAYF(N) MPCB_LAYF(Nother) MPCB_LAYF(Nstc) MPCB_LAYF(nedge) MPCB_LAYF(Ndyn)
     MPCB_LAYF(o_hdr) MPCB_LAYF(o_rv) MPCB_LAYF(o_qstc) MPCB_LAYF(o_seg) MPCB_LAYF(o_c0) MPCB_LAYF(o_c)
     MPCB_LAYF(o_poly) MPCB_LAYF(o_e0) MPCB_LAYF(o_et) MPCB_LAYF(o_mg)
-    MPCB_LAYF(f_e0) MPCB_LAYF(f_et) MPCB_LAYF(f_poly) MPCB_LAYF(f_c0) MPCB_LAYF(f_c) MPCB_LAYF(f_imin) MPCB_LAYF(f_seg) MPCB_LAYF(f_seg2)
+    MPCB_LAYF(f_e0) MPCB_LAYF(f_et) MPCB_LAYF(f_poly) MPCB_LAYF(f_c0) MPCB_LAYF(f_c) MPCB_LAYF(f_imin) MPCB_LAYF(f_seg) MPCB_LAYF(f_seg2) MPCB_LAYF(f_bx0) MPCB_LAYF(f_bx1)
     MPCB_LAYF(total)
 #undef MPCB_LAYF
 };
 
 // ---------------------------------------------------------------- team mode
 // Dimension sets with many ellipses (Ndyn >= MPCB_TEAM_MIN_NDYN: the dense-crowd config, 160
-// ellipses x 40 steps) are solved by ONE CTA PER INSTANCE: warp 0 runs the solver exactly as the
-// one-warp kernel does, the other warps of the CTA ("workers") evaluate the ellipse cost terms of
-// every horizon evaluation in a flat (step, group) mapping - worker thread t owns step
-// k = t % N of group g = t / N and visits the candidate ellipses i with i % G == g - while warp 0
-// walks the reference path, the fleet and the polygons.  One instance per SM keeps the part of
-// its scenario block an evaluation touches resident in L1 (the one-warp kernel with 8 instances
-// per SM read it from DRAM every time: 22 stall cycles per issue on the long scoreboard).
-// ARITHMETIC CONTRACT of team mode (mirrored by the laned oracle): the ellipse cost terms of step
-// k are summed per group (in index order, from +0.0), and the G group sums are then added to the
-// step's stage cost / position gradient in group order; G = team_groups(N, Ndyn).  F2 (raw hinges)
-// keeps the one-warp order: workers only flag the ellipses that have a hinge, warp 0 redoes those.
+// ellipses x 40 steps) are solved by CTAs of MPCB_TEAM_WARPS warps: MPCB_TEAM_SOLVERS "solver" warps,
+// each running the solve of one instance exactly as the one-warp kernel does (rollout scans, adjoint
+// scans, PANOC / L-BFGS algebra), share a pool of "worker" warps that evaluate everything of a
+// horizon evaluation that is independent per step, in a flat (step, group) mapping: worker thread t
+// owns step k = t % N of group g = t / N and handles the reference-path segments k+g, k+g+G, ...,
+// the polygons and the ellipses i with i % G == g.  A solver publishes the positions of its pending
+// evaluation and waits; the pool serves the solvers' requests one at a time, so the sequential part
+// of one instance overlaps the parallel part of another.  Two or three instances per SM keep the
+// part of their scenario blocks an evaluation touches resident in L1 (the one-warp kernel with 8
+// instances per SM read it from DRAM every time: 22 stall cycles per issue on the long scoreboard);
+// position-based culling (bounding boxes of the ellipses of a block of 8 steps against the box of
+// the robot's positions in that block) replaces the anchor-based margins, which stop culling when
+// the robot lags behind its reference.
+// ARITHMETIC CONTRACT of team mode (mirrored by the laned oracle, G = team_groups(N, Ndyn)):
+//   * the polygon and ellipse terms of step k (cost, position gradient, polygon hinge and its
+//     gradient) are summed per group - polygons first, then ellipses, each in index order, from
+//     +0.0 -, the G group sums are added together in group order (from +0.0), and that total is
+//     added to the step's accumulators;
+//   * the reference-path minimum is exact in any order (ties go to the lowest segment index);
+//   * F2 keeps the one-warp order (F2_i = SP + butterfly over the lanes of the step hinges), and the
+//     F2 share of the gradient of an ellipse with a raw hinge somewhere is
+//     fx_k = fma(c F2_i, a.hrx + b.hrx, fx_k) for every step k (both slots added first).
 #ifndef MPCB_TEAM_WARPS
 #define MPCB_TEAM_WARPS 12
+#endif
+#ifndef MPCB_TEAM_SOLVERS
+#define MPCB_TEAM_SOLVERS 2
 #endif
 #ifndef MPCB_TEAM_MIN_NDYN
 #define MPCB_TEAM_MIN_NDYN 64
 #endif
+#ifndef MPCB_TEAM_SLOTS
+#define MPCB_TEAM_SLOTS 8        // hinge rows handed from the workers to a solver per evaluation; ellipses
+                                 // with a hinge beyond that are redone by the solver warp (same values)
+#endif
+#ifndef MPCB_SPIN_SOLVER
+#define MPCB_SPIN_SOLVER            // busy wait (a __nanosleep here costs far more than it saves)
+#endif
+#ifndef MPCB_SPIN_LEADER
+#define MPCB_SPIN_LEADER
+#endif
 constexpr int TEAM_THREADS = 32 * MPCB_TEAM_WARPS;
+constexpr int TEAM_NS = MPCB_TEAM_SOLVERS;
+constexpr int TEAM_WORKERS = TEAM_THREADS - 32 * TEAM_NS;      // worker threads
+#ifndef MPCB_TEAM_CTAS
+#define MPCB_TEAM_CTAS (12 / MPCB_TEAM_WARPS)     // resident teams per SM the register budget is cut for
+#endif
 // number of worker groups (a power of two <= 32 with G*N <= worker threads); 0: one-warp kernel
 __host__ __device__ constexpr int team_groups(int N, int Ndyn)
 {
     if (Ndyn < MPCB_TEAM_MIN_NDYN) return 0;
     int g = 1;
-    while (2 * g <= 32 && 2 * g * N <= 32 * (MPCB_TEAM_WARPS - 1)) g *= 2;
+    while (2 * g <= 32 && 2 * g * N <= TEAM_WORKERS) g *= 2;
     return g;
 }
+// Per-solver block: header, then X[N], Y[N] (request), SUM[6][N] (totals over the groups: cost, gx,
+// gy, polygon hinge, its gradient), PATH[3][N] (path cost, gradient), HROW[SLOTS][N][3] (hinge, hrx,
+// hry of the flagged ellipses) (results).
 struct TeamShared {
     const double* S;       // scenario block of the instance being solved
-    int cmd;               // 1: evaluate, 0: exit
     int grad;              // gradient wanted
-    unsigned cand[8];      // candidate ellipses of this evaluation (one bit each, Ndyn <= 256)
-    unsigned hit[8];       // ellipses with a raw hinge at some step (set by the workers)
+    volatile int req;      // requests published by the solver ...
+    volatile int done;     // ... and served by the pool
+    volatile int exit_;    // the solver has no more instances
+    int pad[6];
+    unsigned hit[8];       // ellipses with a raw hinge at some step (set by the workers; Ndyn <= 256)
 };
 static_assert(sizeof(TeamShared) == 80, "TeamShared is 10 doubles");
-// doubles of team scratch: header, X[N], Y[N], partial sums [3][G][N], D[N] (float)
-__host__ __device__ constexpr int team_doubles(int N, int G)
+struct TeamPtr { double *X, *Y, *SUM, *PATH, *HROW; };
+__host__ __device__ constexpr int team_solver_doubles(int N)
 {
-    return 10 + 2 * N + 3 * G * N + (N + 1) / 2;
+    return (10 + 2 * N + 6 * N + 3 * N + 3 * MPCB_TEAM_SLOTS * N + 1) & ~1;   // even: 16-byte granularity
 }
-__device__ __forceinline__ double* team_X(TeamShared* T) { return reinterpret_cast<double*>(T) + 10; }
+__device__ __forceinline__ TeamPtr team_ptrs(TeamShared* T, int N)
+{
+    TeamPtr q;
+    q.X = reinterpret_cast<double*>(T) + 10;
+    q.Y = q.X + N;
+    q.SUM = q.Y + N;
+    q.PATH = q.SUM + 6 * N;
+    q.HROW = q.PATH + 3 * N;
+    return q;
+}
+// Worker pool scratch: the solver being served, PART[6][G][N] (group sums), PB[G][N] / PI[G][N]
+// (reference-path minimum and argmin per group).
+struct TeamPool { volatile int cur; int pad[3]; };
+__host__ __device__ constexpr int team_pool_doubles(int N, int G)
+{
+    return 2 + 6 * G * N + G * N + (G * N + 1) / 2;
+}
+// shared memory of a team CTA (doubles): per solver its warp scratch (lb_doubles) and its team
+// block, then the pool
+__host__ __device__ constexpr int team_smem_doubles(int N, int G, int lb_doubles, int solvers)
+{
+    return solvers * (lb_doubles + team_solver_doubles(N)) + team_pool_doubles(N, G);
+}
 __device__ __forceinline__ void bar_sync(int id, int nthreads)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -555,24 +617,26 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
         if (__any_sync(FULL, bad)) dmax = __int_as_float(0x7f800000);   // non-finite state: cull nothing
     }
     if constexpr (TEAM) {
-        // hand the positions and the candidate ellipses to the workers, then walk the path, the
-        // fleet and the polygons while they evaluate the ellipse cost terms
-        double* TX = team_X(T);
-        double* TY = TX + N;
-        float* TD = reinterpret_cast<float*>(TY + N + 3 * team_groups(N, L.Ndyn()) * N);
-        const float* ime = MG + L.f_imin();
+        // hand the positions to the worker pool and wait for its share of the evaluation
+        const TeamPtr tp = team_ptrs(T, N);
 #pragma unroll
         for (int j = 0; j < SPL; ++j)
-            if (act[j]) { TX[kk[j]] = X[j]; TY[kk[j]] = Y[j]; TD[kk[j]] = Df[j]; }
-#pragma unroll 1
-        for (int base = 0; base < L.Ndyn(); base += 32) {
-            const int it = base + lane;
-            const unsigned mk = __ballot_sync(FULL, it < L.Ndyn() && !(ime[it < L.Ndyn() ? it : 0] > dmax));
-            if (lane == 0) { T->cand[base >> 5] = mk; T->hit[base >> 5] = 0u; }
-        }
-        if (lane == 0) { T->S = S; T->grad = GRAD ? 1 : 0; T->cmd = 1; }
+            if (act[j]) { tp.X[kk[j]] = X[j]; tp.Y[kk[j]] = Y[j]; }
+        if (lane < 8) T->hit[lane] = 0u;
         __syncwarp();
-        bar_sync(1, TEAM_THREADS);
+        // every lane waits in the same (warp-uniform) loop: a spin loop under `if (lane == 0)` leaves
+        // the warp split into two convergence groups for the rest of the evaluation
+        const int r = T->req + 1;
+        __syncwarp();
+        if (lane == 0) {
+            T->S = S; T->grad = GRAD ? 1 : 0;
+            __threadfence_block();
+            T->req = r;
+        }
+        __syncwarp();
+        while (T->done != r) { MPCB_SPIN_SOLVER; }
+        __threadfence_block();
+        __syncwarp();
     }
     const float* IM_E = MG + L.f_imin();
     const float* IM_P = IM_E + L.Ndyn();
@@ -589,7 +653,10 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
         // -- reference path: qrpd * min_{i>=k} dist^2(p, seg_i)   (mpc_cost.py:84-95).
         //    Segments are visited from i = k; the walk stops once the precomputed bound
         //    says no later segment can beat the current minimum.
-        {
+        if constexpr (TEAM) {       // the workers did it
+            const TeamPtr tp = team_ptrs(T, N);
+            cst = tp.PATH[k]; ggx = tp.PATH[N + k]; ggy = tp.PATH[2 * N + k];
+        } else {
             const float* tm = MG + L.f_seg() + k * N;
             const float* tm2 = MG + L.f_seg2() + k * N;
             const float Pj = Pf[j];
@@ -680,7 +747,7 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
         }
         // -- static polygons (mpc_builder.py:100-108)
         double sp = 0.0, spx = 0.0, spy = 0.0;
-        {
+        if constexpr (!TEAM) {
             const double qs = S[L.o_qstc() + k];
             const double* pe = S + L.o_poly();
             const float* mp = MG + L.f_poly() + k;
@@ -723,19 +790,15 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
     //      gradient once at the end, so the order of the cost-gradient sum does not depend on
     //      which obstacles are hit.
     if constexpr (TEAM) {
-        // the workers' group sums of the ellipse cost terms, added in group order
-        __syncwarp();
-        bar_sync(2, TEAM_THREADS);
-        const int G = team_groups(N, L.Ndyn());
-        const double* PC = team_X(T) + 2 * N;
+        // the workers' totals of the polygon and ellipse terms of every step
+        const double* SUM = team_ptrs(T, N).SUM;
 #pragma unroll
         for (int j = 0; j < SPL; ++j) {
             if (act[j]) {
-#pragma unroll 1
-                for (int g = 0; g < G; ++g) {
-                    cstj[j] += PC[g * N + kk[j]];
-                    if (GRAD) { gx[j] += PC[(G + g) * N + kk[j]]; gy[j] += PC[(2 * G + g) * N + kk[j]]; }
-                }
+                const double* q = SUM + kk[j];
+                cstj[j] += q[0];
+                Spoly[j] = q[3 * N];
+                if (GRAD) { gx[j] += q[N]; gy[j] += q[2 * N]; dSx[j] = q[4 * N]; dSy[j] = q[5 * N]; }
             }
         }
     }
@@ -750,6 +813,7 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
         const double SP = anyp ? warp_sum(spl) : 0.0;
         anyF2 = anyp || F2out != nullptr;
         int nxt = 0;     // F2 entries [0, nxt) are accounted for
+        int nflag = 0;   // team mode: flagged ellipses met so far (= the row the workers filled)
         const double* e0 = S + L.o_e0();
         const double* etb = S + L.o_et();
         const float* me0b = MG + L.f_e0();
@@ -765,28 +829,54 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
                 mk &= mk - 1;
                 EllT a[SPL], b[SPL];
                 double hl = 0.0;
+                double hx[SPL], hy[SPL];      // team mode: a.hrx + b.hrx, a.hry + b.hry
+                bool from_row = false;
+                if constexpr (TEAM) {
+                    // flagged ellipses arrive as rows (hinge, hrx, hry per step) from the workers
+                    if (nflag < MPCB_TEAM_SLOTS) {
+                        const double* row = team_ptrs(T, N).HROW + (size_t)nflag * N * 3;
 #pragma unroll
-                for (int j = 0; j < SPL; ++j) {
-                    const int k = act[j] ? kk[j] : N - 1;
-                    a[j].hr = 0.0; b[j].hr = 0.0;
-                    if (!(me0b[i * N + k] > Df[j])) {          // t = 0 slot (one ellipse for all steps)
-                        ellipse_terms(GRAD, e0 + i, L.Ndyn(), X[j], Y[j], a[j]);
-                        if constexpr (!TEAM) {
-                            cstj[j] += a[j].cost;
-                            if (GRAD) { gx[j] += a[j].gx; gy[j] += a[j].gy; }
+                        for (int j = 0; j < SPL; ++j) {
+                            hx[j] = 0.0; hy[j] = 0.0;
+                            if (act[j]) {
+                                const double* r = row + 3 * kk[j];
+                                hl += r[0]; hx[j] = r[1]; hy[j] = r[2];
+                            }
+                        }
+                        from_row = true;
+                    }
+                    ++nflag;
+                }
+                if (!from_row) {
+#pragma unroll
+                    for (int j = 0; j < SPL; ++j) {
+                        const int k = act[j] ? kk[j] : N - 1;
+                        a[j].hr = 0.0; b[j].hr = 0.0; a[j].hrx = 0.0; a[j].hry = 0.0; b[j].hrx = 0.0; b[j].hry = 0.0;
+                        if (!(me0b[i * N + k] > Df[j])) {          // t = 0 slot (one ellipse for all steps)
+                            ellipse_terms(GRAD, e0 + i, L.Ndyn(), X[j], Y[j], a[j]);
+                            if constexpr (!TEAM) {
+                                cstj[j] += a[j].cost;
+                                if (GRAD) { gx[j] += a[j].gx; gy[j] += a[j].gy; }
+                            }
+                        }
+                        if (!(metb[i * N + k] > Df[j])) {          // t = k+1 slot
+                            ellipse_terms(GRAD, etb + k + i * N, L.Ndyn() * N, X[j], Y[j], b[j]);
+                            if constexpr (!TEAM) {
+                                cstj[j] += b[j].cost;
+                                if (GRAD) { gx[j] += b[j].gx; gy[j] += b[j].gy; }
+                            }
+                        }
+                        if (!act[j]) { a[j].hr = 0.0; b[j].hr = 0.0; }
+                        hl += a[j].hr + b[j].hr;
+                        if constexpr (TEAM) {
+                            hx[j] = act[j] ? a[j].hrx + b[j].hrx : 0.0;
+                            hy[j] = act[j] ? a[j].hry + b[j].hry : 0.0;
                         }
                     }
-                    if (!(metb[i * N + k] > Df[j])) {          // t = k+1 slot
-                        ellipse_terms(GRAD, etb + k + i * N, L.Ndyn() * N, X[j], Y[j], b[j]);
-                        if constexpr (!TEAM) {
-                            cstj[j] += b[j].cost;
-                            if (GRAD) { gx[j] += b[j].gx; gy[j] += b[j].gy; }
-                        }
-                    }
-                    if (!act[j]) { a[j].hr = 0.0; b[j].hr = 0.0; }
-                    hl += a[j].hr + b[j].hr;
                 }
                 if (__any_sync(FULL, hl > 0.0)) {
+                    // (team mode: with SP == +0.0 the catch-up adds exact zeros to non-negative sums)
+                    if (TEAM && SP == 0.0 && !F2out) nxt = i;
 #pragma unroll 1
                     for (; nxt < i; ++nxt) {                   // entries without a hinge equal SP
                         if (F2out && lane == 0) F2out[nxt] = SP;
@@ -803,8 +893,12 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
                         const double m = c * F2i;
 #pragma unroll
                         for (int j = 0; j < SPL; ++j) {
-                            if (a[j].hr > 0.0) { fx[j] = fma(m, a[j].hrx, fx[j]); fy[j] = fma(m, a[j].hry, fy[j]); }
-                            if (b[j].hr > 0.0) { fx[j] = fma(m, b[j].hrx, fx[j]); fy[j] = fma(m, b[j].hry, fy[j]); }
+                            if constexpr (TEAM) {
+                                if (act[j]) { fx[j] = fma(m, hx[j], fx[j]); fy[j] = fma(m, hy[j], fy[j]); }
+                            } else {
+                                if (a[j].hr > 0.0) { fx[j] = fma(m, a[j].hrx, fx[j]); fy[j] = fma(m, a[j].hry, fy[j]); }
+                                if (b[j].hr > 0.0) { fx[j] = fma(m, b[j].hrx, fx[j]); fy[j] = fma(m, b[j].hry, fy[j]); }
+                            }
                         }
                     }
                 }
@@ -815,6 +909,7 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
             sumF2 = SP;
             if (F2out && lane == 0) F2out[0] = SP;
         } else if (anyF2) {
+            if (TEAM && SP == 0.0 && !F2out) nxt = L.Ndyn();
 #pragma unroll 1
             for (; nxt < L.Ndyn(); ++nxt) {
                 if (F2out && lane == 0) F2out[nxt] = SP;
@@ -931,66 +1026,224 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
     }
 }
 
-// Worker threads of a team (every warp of the CTA but warp 0); t = thread index among the workers.
+// Worker threads of a team (every warp of the CTA but the solver warps); t = thread index among the
+// workers, `solvers` = the per-solver blocks (stride `sstride` doubles), NS of them take part.
+// The pool serves one request at a time (worker thread 0 picks the next pending one, round robin):
+// pass 1 (path segments, polygons and ellipses of the thread's step and group; group sums; ellipses
+// with a raw hinge flagged), a barrier among the workers, pass 2 (totals over the groups; path
+// minimum over the groups and its gradient; hinge rows of the flagged ellipses), a barrier, and the
+// request is marked done.
 template <int FIXED>
-__device__ __forceinline__ void team_worker(const KParams& P, TeamShared* T, int t)
+__device__ __forceinline__ void team_worker(const KParams& P, double* solvers, int sstride, int lb_doubles,
+                                            int NS, TeamPool* pool, int t)
 {
     const LayV<FIXED> L{&P.L};
     const int N = L.N(), Ndyn = L.Ndyn();
     const int G = team_groups(N, Ndyn);
-    const double* TX = team_X(T);
-    const double* TY = TX + N;
-    double* PC = team_X(T) + 2 * N;
-    const float* TD = reinterpret_cast<const float*>(PC + 3 * G * N);
+    double* const PART = reinterpret_cast<double*>(pool) + 2;
+    double* const PB = PART + 6 * G * N;
+    int* const PI = reinterpret_cast<int*>(PB + G * N);
     const bool mine = t < G * N;
     const int g = t / N, k = mine ? t - g * N : 0;
     unsigned cls = 0u;                       // ellipses i with i % G == g (G divides 32)
     for (int b = g; b < 32; b += G) cls |= 1u << b;
+    const bool CULL = P.cull != 0;
+    const int NB = (N + 7) >> 3, blk = k >> 3;
+    int last = NS - 1;
     for (;;) {
-        bar_sync(1, TEAM_THREADS);
-        if (T->cmd == 0) return;
+        if (t < 32) {
+            // next pending request, round robin from the solver served last; -1 when every solver is
+            // done.  The whole first worker warp polls (warp-uniform loop, broadcast loads).
+            int pick = -2;
+            while (pick == -2) {
+                int nexit = 0;
+                for (int q = 1; q <= NS; ++q) {
+                    int s = last + q;
+                    if (s >= NS) s -= NS;
+                    TeamShared* Ts = reinterpret_cast<TeamShared*>(solvers + (size_t)s * sstride + lb_doubles);
+                    if (Ts->req != Ts->done) { pick = s; break; }
+                    nexit += Ts->exit_;
+                }
+                if (pick == -2) {
+                    if (nexit == NS) pick = -1;
+                    else { MPCB_SPIN_LEADER; }
+                }
+            }
+            pick = __shfl_sync(FULL, pick, 0);     // one decision for the warp
+            __threadfence_block();
+            if (t == 0) pool->cur = pick;
+        }
+        __syncwarp();
+        bar_sync(3, TEAM_WORKERS);
+        const int cur = pool->cur;
+        if (cur < 0) return;
+        last = cur;
+        TeamShared* T = reinterpret_cast<TeamShared*>(solvers + (size_t)cur * sstride + lb_doubles);
+        const TeamPtr tp = team_ptrs(T, N);
+        const double* __restrict__ S = T->S;
+        const bool GRAD = T->grad != 0;
+        const float* MG = reinterpret_cast<const float*>(S + L.o_mg());
+        const double* e0 = S + L.o_e0();
+        const double* etb = S + L.o_et() + k;
+        const float4* bx0 = reinterpret_cast<const float4*>(MG + L.f_bx0());
+        const float4* bx1 = reinterpret_cast<const float4*>(MG + L.f_bx1()) + blk;
+        const double x = tp.X[k], y = tp.Y[k];
+        // bounding box of the robot's positions over this step's block of 8 steps, rounded outwards
+        float rx0, rx1, ry0, ry1;
+        {
+            const int ka = blk << 3, kb = ka + 8 < N ? ka + 8 : N;
+            double a0 = tp.X[ka], a1 = a0, b0 = tp.Y[ka], b1 = b0;
+            bool bad = !(a0 == a0) || !(b0 == b0);
+#pragma unroll 1
+            for (int q = ka + 1; q < kb; ++q) {
+                const double xq = tp.X[q], yq = tp.Y[q];
+                bad |= !(xq == xq) || !(yq == yq);
+                a0 = xq < a0 ? xq : a0; a1 = xq > a1 ? xq : a1;
+                b0 = yq < b0 ? yq : b0; b1 = yq > b1 ? yq : b1;
+            }
+            rx0 = __double2float_rd(a0); rx1 = __double2float_ru(a1);
+            ry0 = __double2float_rd(b0); ry1 = __double2float_ru(b1);
+            if (bad || !CULL) { rx0 = ry0 = -__int_as_float(0x7f800000); rx1 = ry1 = __int_as_float(0x7f800000); }
+        }
         if (mine) {
-            const double* __restrict__ S = T->S;
-            const bool GRAD = T->grad != 0;
-            const float* MG = reinterpret_cast<const float*>(S + L.o_mg());
-            const float* me0b = MG + L.f_e0() + k;
-            const float* metb = MG + L.f_et() + k;
-            const double* e0 = S + L.o_e0();
-            const double* etb = S + L.o_et() + k;
-            const double x = TX[k], y = TY[k];
-            const float D = TD[k];
-            double pc = 0.0, pgx = 0.0, pgy = 0.0;
+            // ---- pass 1a: reference path, segments k+g, k+g+G, ... (mpc_cost.py:84-95)
+            {
+                const double* sg = S + L.o_seg();
+                double best = INFINITY;
+                int ib = N;
+#pragma unroll 1
+                for (int i = k + g; i < N; i += G) {
+                    const double ex = x - sg[i], ey = y - sg[N + i];
+                    const double ddx = sg[2 * N + i], ddy = sg[3 * N + i];
+                    const double th_ = fma(ex, ddx, ey * ddy) * sg[4 * N + i];
+                    const double ts_ = clamp01(th_);
+                    const double vx = fma(ts_, ddx, -ex), vy = fma(ts_, ddy, -ey);
+                    const double d2 = fma(vx, vx, vy * vy);
+                    if (d2 < best) { best = d2; ib = i; }
+                }
+                PB[g * N + k] = best;
+                PI[g * N + k] = ib;
+            }
+            // ---- pass 1b: polygons i % G == g (mpc_builder.py:100-108), then ellipses i % G == g
+            double pc = 0.0, pgx = 0.0, pgy = 0.0, psp = 0.0, pspx = 0.0, pspy = 0.0;
+            {
+                const double qs = S[L.o_qstc() + k];
+                const double* pe = S + L.o_poly();
+#pragma unroll 1
+                for (int i = g; i < L.Nstc(); i += G) {
+                    double dIx, dIy;
+                    const double I = polygon_ind(GRAD, pe + i * 3 * L.nedge(), L.nedge(), x, y, dIx, dIy);
+                    if (I > 0.0) {
+                        pc = fma(qs, I * I, pc);
+                        psp += I;
+                        if (GRAD) {
+                            const double m = 2.0 * qs * I;
+                            pgx = fma(m, dIx, pgx);
+                            pgy = fma(m, dIy, pgy);
+                            pspx += dIx;
+                            pspy += dIy;
+                        }
+                    }
+                }
+            }
+#pragma unroll 2
+            for (int i = g; i < Ndyn; i += G) {
+                // an ellipse whose bounding box misses the block's robot box is exactly zero at
+                // every step of the block (NaN boxes compare false: never skipped)
+                const float4 q0 = bx0[i], q1 = bx1[i * NB];
+                const bool in0 = !(rx0 > q0.y || rx1 < q0.x || ry0 > q0.w || ry1 < q0.z);
+                const bool in1 = !(rx0 > q1.y || rx1 < q1.x || ry0 > q1.w || ry1 < q1.z);
+                EllT a, b;
+                a.hr = 0.0; b.hr = 0.0;
+                if (in0) {                               // t = 0 slot
+                    ellipse_terms(GRAD, e0 + i, Ndyn, x, y, a);
+                    pc += a.cost;
+                    if (GRAD) { pgx += a.gx; pgy += a.gy; }
+                }
+                if (in1) {                               // t = k+1 slot
+                    ellipse_terms(GRAD, etb + i * N, Ndyn * N, x, y, b);
+                    pc += b.cost;
+                    if (GRAD) { pgx += b.gx; pgy += b.gy; }
+                }
+                if (a.hr > 0.0 || b.hr > 0.0) atomicOr(&T->hit[i >> 5], 1u << (i & 31));
+            }
+            double* q = PART + g * N + k;
+            q[0] = pc; q[G * N] = pgx; q[2 * G * N] = pgy;
+            q[3 * G * N] = psp; q[4 * G * N] = pspx; q[5 * G * N] = pspy;
+        }
+        __syncwarp();
+        bar_sync(3, TEAM_WORKERS);
+        // ---- pass 2a: totals over the groups, in group order from +0.0 (6 quantities x N steps)
+#pragma unroll 1
+        for (int idx = t; idx < 6 * N; idx += TEAM_WORKERS) {
+            const int qn = idx / N, kq = idx - qn * N;
+            const double* q = PART + qn * G * N + kq;
+            double tot = 0.0;
+#pragma unroll 1
+            for (int gg = 0; gg < G; ++gg) tot += q[gg * N];
+            tp.SUM[idx] = tot;
+        }
+        if (mine) {
+            // ---- pass 2b (group G-1: the threads pass 2a leaves idle first): path minimum over the
+            //      groups (ties: lowest index), cost, gradient
+            if (g == G - 1) {
+                const double* sg = S + L.o_seg();
+                const double qrpd = S[L.o_hdr() + H_Q + 7];
+                double best = INFINITY;
+                int ib = k;
+#pragma unroll 1
+                for (int gg = 0; gg < G; ++gg) {
+                    const double bq = PB[gg * N + k];
+                    const int iq = PI[gg * N + k];
+                    if (bq < best || (bq == best && iq < ib)) { best = bq; ib = iq; }
+                }
+                double ggx = 0.0, ggy = 0.0;
+                if (GRAD) {
+                    const double ex = x - sg[ib], ey = y - sg[N + ib];
+                    const double ddx = sg[2 * N + ib], ddy = sg[3 * N + ib], inv = sg[4 * N + ib];
+                    const double th_ = fma(ex, ddx, ey * ddy) * inv;
+                    const double ts_ = clamp01(th_);
+                    const double vx = fma(ts_, ddx, -ex), vy = fma(ts_, ddy, -ey);
+                    const double dt = (th_ > 0.0 && th_ < 1.0) ? 1.0 : ((th_ == 0.0 || th_ == 1.0) ? 0.5 : 0.0);
+                    const double vd = fma(vx, ddx, vy * ddy) * dt * inv;
+                    ggx = 2.0 * qrpd * fma(vd, ddx, -vx);
+                    ggy = 2.0 * qrpd * fma(vd, ddy, -vy);
+                }
+                tp.PATH[k] = best * qrpd; tp.PATH[N + k] = ggx; tp.PATH[2 * N + k] = ggy;
+            }
+            // ---- pass 2c: hinge rows of the flagged ellipses of this group (row = rank of the ellipse
+            //      among the flagged ones), as far as there are rows
+            int below = 0;
 #pragma unroll 1
             for (int base = 0; base < Ndyn; base += 32) {
-                unsigned m = T->cand[base >> 5] & cls;
-                unsigned hits = 0u;
+                const unsigned hw = T->hit[base >> 5];
+                unsigned m = hw & cls;
 #pragma unroll 1
                 while (m) {
                     const int bit = __ffs(m) - 1;
                     const int i = base + bit;
                     m &= m - 1;
+                    const int slot = below + __popc(hw & ((1u << bit) - 1u));
+                    if (slot >= MPCB_TEAM_SLOTS) break;
+                    const float4 q0 = bx0[i], q1 = bx1[i * NB];
+                    const bool in0 = !(rx0 > q0.y || rx1 < q0.x || ry0 > q0.w || ry1 < q0.z);
+                    const bool in1 = !(rx0 > q1.y || rx1 < q1.x || ry0 > q1.w || ry1 < q1.z);
                     EllT a, b;
-                    a.hr = 0.0; b.hr = 0.0;
-                    if (!(me0b[i * N] > D)) {              // t = 0 slot
-                        ellipse_terms(GRAD, e0 + i, Ndyn, x, y, a);
-                        pc += a.cost;
-                        if (GRAD) { pgx += a.gx; pgy += a.gy; }
-                    }
-                    if (!(metb[i * N] > D)) {              // t = k+1 slot
-                        ellipse_terms(GRAD, etb + i * N, Ndyn * N, x, y, b);
-                        pc += b.cost;
-                        if (GRAD) { pgx += b.gx; pgy += b.gy; }
-                    }
-                    if (a.hr > 0.0 || b.hr > 0.0) hits |= 1u << bit;
+                    a.hr = 0.0; a.hrx = 0.0; a.hry = 0.0; b.hr = 0.0; b.hrx = 0.0; b.hry = 0.0;
+                    if (in0) ellipse_terms(GRAD, e0 + i, Ndyn, x, y, a);
+                    if (in1) ellipse_terms(GRAD, etb + i * N, Ndyn * N, x, y, b);
+                    double* r = tp.HROW + ((size_t)slot * N + k) * 3;
+                    r[0] = a.hr + b.hr; r[1] = a.hrx + b.hrx; r[2] = a.hry + b.hry;
                 }
-                if (hits) atomicOr(&T->hit[base >> 5], hits);
+                below += __popc(hw);
             }
-            PC[g * N + k] = pc;
-            PC[(G + g) * N + k] = pgx;
-            PC[(2 * G + g) * N + k] = pgy;
         }
         __syncwarp();
-        bar_sync(2, TEAM_THREADS);
+        bar_sync(3, TEAM_WORKERS);
+        if (t == 0) {
+            __threadfence_block();
+            T->done = T->req;
+        }
     }
 }
 

@@ -60,9 +60,10 @@ struct Inst {   // per-lane slice of the solver state of one instance
 };
 
 // Outer-loop (ALM) state of one instance: touched once per outer iteration, so it lives in the
-// warp's shared-memory scratch for good.  Every lane writes the same value; every read-modify-write
-// of a field is preceded by __syncwarp() (convergence + memory ordering), so no lane can read a value
-// another lane has already incremented.
+// warp's shared-memory scratch for good.  Fields are read by every lane; every read-modify-write is
+// done by lane 0 alone between two __syncwarp() (MPCB_CS_LANE0): under independent thread scheduling
+// a lane that runs late (after a divergent walk, or lane 0 after waiting for the worker pool) must
+// not read a value another lane has already incremented.
 struct ColdState {
     double c;                      // penalty
     double akkt_tol;
@@ -78,6 +79,7 @@ __host__ __device__ constexpr int scratch_doubles(int N)
 }
 
 #define MPCB_FORJ _Pragma("unroll") for (int j = 0; j < SPL; ++j)
+#define MPCB_CS_LANE0(...) do { __syncwarp(); if (lane == 0) { __VA_ARGS__; } __syncwarp(); } while (0)
 
 template <int SPL>
 __device__ __forceinline__ double sumsq2(const double (&a)[SPL], const double (&b)[SPL])
@@ -319,7 +321,7 @@ L_outer_begin:   // ---- AlmOptimizer::step: project y on Y, then the inner prob
     // AlmOptimizer::solve checks the remaining time before every outer iteration; here the clock
     // is the inner-iteration count (cfg->max_inner_total, 0 = off)
     if (P.budget > 0 && CS->inner_total >= P.budget) { CS->status = MPCB_NOT_CONVERGED_OUT_OF_TIME; goto L_finish; }
-    CS->n_outer = CS->n_outer + 1;
+    MPCB_CS_LANE0(CS->n_outer = CS->n_outer + 1);
     MPCB_FORJ {
         const int k = lane + 32 * j;
         double ya_ = 0.0, yw_ = 0.0;
@@ -368,7 +370,7 @@ L_eval:
     ls = reinterpret_cast<int*>(spark + 8)[2];
     B.head = reinterpret_cast<int*>(spark + 8)[3];
     B.active = reinterpret_cast<int*>(spark + 8)[4];
-    if (want_grad) CS->n_grad = CS->n_grad + 1; else CS->n_cost = CS->n_cost + 1;
+    MPCB_CS_LANE0(if (want_grad) CS->n_grad = CS->n_grad + 1; else CS->n_cost = CS->n_cost + 1);
     switch (st) {
         case ST_INIT: goto H_INIT;
         case ST_INIT_LIP: goto H_INIT_LIP;
@@ -535,7 +537,7 @@ L_step_return:   // PANOCOptimizer::solve: flag = step(); while (flag && cont) {
     CS->inner = cont ? MPCB_CONVERGED
                      : (num_iter >= P.max_inner ? MPCB_NOT_CONVERGED_ITERATIONS : MPCB_NOT_CONVERGED_OUT_OF_TIME);
     CS->last_fpr = I.norm_r;
-    CS->inner_total = CS->inner_total + num_iter;
+    MPCB_CS_LANE0(CS->inner_total = CS->inner_total + num_iter);
     // F1(u), F2(u), f(u) at the inner solution: one horizon evaluation with c = 0
     MPCB_FORJ { pt0[j] = I.u0[j]; pt1[j] = I.u1[j]; }
     want_grad = false; ceff = 0.0; st = ST_ALM;
@@ -565,31 +567,46 @@ H_ALM: {
         dsum = fma(e0, e0, fma(e1, e1, dsum));
     }
     const double dy_plus = sqrt(warp_sum(dsum));
-    CS->fcost = fcost; CS->f2n_plus = f2n_plus; CS->dy_plus = dy_plus;
-    // is_exit_criterion_satisfied
+    // every lane reads what it needs of the outer-loop state, then lane 0 alone updates it
     const int alm_iter = CS->alm_iter;
     const double akkt_tol = CS->akkt_tol;
+    const double dy_old = CS->dy, f2n_old = CS->f2n;
+    const int inner_st = CS->inner;
+    // is_exit_criterion_satisfied
     const bool c1 = alm_iter > 0 && dy_plus <= cpen * P.delta + EPS;
     const bool c2 = f2n_plus <= P.delta + EPS;
     const bool c3 = akkt_tol <= P.tol + EPS;
-    if (c1 && c2 && c3) { CS->status = CS->inner; goto L_finish; }
     // is_penalty_stall_criterion
-    const bool stall = alm_iter == 0 || (dy_plus <= P.theta * CS->dy + EPS && f2n_plus <= P.theta * CS->f2n + EPS);
-    if (!stall) CS->c = cpen * P.rho;
-    CS->akkt_tol = fmax(akkt_tol * P.beta, P.tol);
-    CS->alm_iter = alm_iter + 1;
-    CS->dy = dy_plus;
-    CS->f2n = f2n_plus;
+    const bool stall = alm_iter == 0 || (dy_plus <= P.theta * dy_old + EPS && f2n_plus <= P.theta * f2n_old + EPS);
+    const bool exit_now = c1 && c2 && c3;
+    MPCB_CS_LANE0(
+        CS->fcost = fcost; CS->f2n_plus = f2n_plus; CS->dy_plus = dy_plus;
+        if (exit_now) CS->status = inner_st;
+        else {
+            if (!stall) CS->c = cpen * P.rho;
+            CS->akkt_tol = fmax(akkt_tol * P.beta, P.tol);
+            CS->alm_iter = alm_iter + 1;
+            CS->dy = dy_plus;
+            CS->f2n = f2n_plus;
+        });
+    if (exit_now) goto L_finish;
     MPCB_FORJ {
         const int k = lane + 32 * j;
         if (act[j]) { ysm[k] = ypsm[k]; ysm[N + k] = ypsm[N + k]; }
     }
-    if (CS->outer < P.max_outer) { CS->outer = CS->outer + 1; goto L_outer_begin; }
+    {
+        const bool more = CS->outer < P.max_outer;
+        MPCB_CS_LANE0(if (more) CS->outer = CS->outer + 1);
+        if (more) goto L_outer_begin;
+    }
     goto L_finish;
 }
 
 L_finish:
-    if (!CS->failed && CS->n_outer == P.max_outer) CS->status = MPCB_NOT_CONVERGED_ITERATIONS;
+    {
+        const bool capped = !CS->failed && CS->n_outer == P.max_outer;
+        MPCB_CS_LANE0(if (capped) CS->status = MPCB_NOT_CONVERGED_ITERATIONS);
+    }
     MPCB_FORJ {
         const int k = lane + 32 * j;
         if (act[j]) {

@@ -158,15 +158,17 @@ static double dotw(int J, lanes_t a0, lanes_t a1, lanes_t b0, lanes_t b1)
 }
 
 /* Team mode (arithmetic contract, csrc/mpcb_device.cuh "team mode"): dimension sets with at
- * least 64 ellipses are solved by a 12-warp CTA per instance whose 11 worker warps own
- * (step, group) pairs; the number of groups is the largest power of two G <= 32 with
- * G*N <= 352.  The ellipse cost terms of a step are summed per group i % G (index order, from
- * +0.0) and the group sums are added to the step's stage cost / gradient in group order. */
+ * least 64 ellipses are solved by 12-warp CTAs whose 10 worker warps own (step, group) pairs;
+ * the number of groups is the largest power of two G <= 32 with G*N <= 320.  The polygon and
+ * ellipse terms of a step are summed per group i % G (polygons, then ellipses, index order, from
+ * +0.0), the group sums are added together in group order (from +0.0) and the total is added to
+ * the step's accumulators; the F2 share of the gradient adds both slots of an ellipse before the
+ * fma. */
 int32_t mpcl_team_groups(const mpcb_dims* d)
 {
     if (d->Ndyn < 64) return 0;
     int g = 1;
-    while (2 * g <= 32 && 2 * g * d->N <= 32 * 11) g *= 2;
+    while (2 * g <= 32 && 2 * g * d->N <= 32 * 10) g *= 2;
     return g;
 }
 
@@ -418,7 +420,7 @@ static void eval_psi(const scen_t* S, lanes_t v, lanes_t w, double c, lanes_t ya
                 cst = fma(10.0, s2, cst);
             }
             double sp = 0.0, spx = 0.0, spy = 0.0;
-            {   /* static polygons */
+            if (S->G == 0) {   /* static polygons, then dynamic ellipses, one chain per step */
                 const double qs = S->qstc[k];
                 for (int i = 0; i < S->Nstc; ++i) {
                     double dIx, dIy;
@@ -435,9 +437,7 @@ static void eval_psi(const scen_t* S, lanes_t v, lanes_t w, double c, lanes_t ya
                         }
                     }
                 }
-            }
-            if (S->G == 0) {
-                for (int i = 0; i < S->Ndyn; ++i) {   /* dynamic ellipses */
+                for (int i = 0; i < S->Ndyn; ++i) {
                     ell_t a, b;
                     ellipse_terms(GRAD, S->e0 + i, S->Ndyn, x, y, &a);
                     cst += a.cost;
@@ -446,9 +446,28 @@ static void eval_psi(const scen_t* S, lanes_t v, lanes_t w, double c, lanes_t ya
                     cst += b.cost;
                     if (GRAD) { ggx += b.gx; ggy += b.gy; }
                 }
-            } else {                                  /* team mode: per-group sums first */
-                double pc[32], pgx[32], pgy[32];
-                for (int g = 0; g < S->G; ++g) { pc[g] = 0.0; pgx[g] = 0.0; pgy[g] = 0.0; }
+            } else {
+                /* team mode: group g sums the polygons i % G == g, then the ellipses i % G == g
+                   (index order, from +0.0); the group sums are added in group order */
+                const double qs = S->qstc[k];
+                double pc[32], pgx[32], pgy[32], psp[32], pspx[32], pspy[32];
+                for (int g = 0; g < S->G; ++g) { pc[g] = 0.0; pgx[g] = 0.0; pgy[g] = 0.0; psp[g] = 0.0; pspx[g] = 0.0; pspy[g] = 0.0; }
+                for (int i = 0; i < S->Nstc; ++i) {
+                    const int g = i % S->G;
+                    double dIx, dIy;
+                    const double I = polygon_ind(GRAD, S->poly + i * 3 * S->nedge, S->nedge, x, y, &dIx, &dIy);
+                    if (I > 0.0) {
+                        pc[g] = fma(qs, I * I, pc[g]);
+                        psp[g] += I;
+                        if (GRAD) {
+                            const double m = 2.0 * qs * I;
+                            pgx[g] = fma(m, dIx, pgx[g]);
+                            pgy[g] = fma(m, dIy, pgy[g]);
+                            pspx[g] += dIx;
+                            pspy[g] += dIy;
+                        }
+                    }
+                }
                 for (int i = 0; i < S->Ndyn; ++i) {
                     const int g = i % S->G;
                     ell_t a, b;
@@ -459,10 +478,14 @@ static void eval_psi(const scen_t* S, lanes_t v, lanes_t w, double c, lanes_t ya
                     pc[g] += b.cost;
                     if (GRAD) { pgx[g] += b.gx; pgy[g] += b.gy; }
                 }
+                double tc = 0.0, tgx = 0.0, tgy = 0.0;
                 for (int g = 0; g < S->G; ++g) {
-                    cst += pc[g];
-                    if (GRAD) { ggx += pgx[g]; ggy += pgy[g]; }
+                    tc += pc[g];
+                    sp += psp[g];
+                    if (GRAD) { tgx += pgx[g]; tgy += pgy[g]; spx += pspx[g]; spy += pspy[g]; }
                 }
+                cst += tc;
+                if (GRAD) { ggx += tgx; ggy += tgy; }
             }
             if (!act[j][l]) { cst = 0.0; ggx = 0.0; ggy = 0.0; sp = 0.0; spx = 0.0; spy = 0.0; gvd[j][l] = 0.0; gwd[j][l] = 0.0; }
             cost[l] += cst;
@@ -528,13 +551,24 @@ static void eval_psi(const scen_t* S, lanes_t v, lanes_t w, double c, lanes_t ya
             if (F2out) F2out[i] = F2i;
             f2sq = fma(F2i, F2i, f2sq);
             sumF2 += F2i;
-            if (GRAD && F2i > 0.0) {
+            if (GRAD && F2i > 0.0 && S->G == 0) {
                 const double m = c * F2i;
                 for (int j = 0; j < J; ++j)
                     for (int l = 0; l < W; ++l) {
                         if (A[j][l].hr > 0.0) { fx[j][l] = fma(m, A[j][l].hrx, fx[j][l]); fy[j][l] = fma(m, A[j][l].hry, fy[j][l]); }
                         if (B[j][l].hr > 0.0) { fx[j][l] = fma(m, B[j][l].hrx, fx[j][l]); fy[j][l] = fma(m, B[j][l].hry, fy[j][l]); }
                     }
+            }
+            if (GRAD && F2i > 0.0 && S->G > 0 && any) {
+                /* team mode: an ellipse with a raw hinge somewhere contributes at every step, both
+                   slots added first (hrx, hry are zero where there is no hinge) */
+                const double m = c * F2i;
+                for (int j = 0; j < J; ++j)
+                    for (int l = 0; l < W; ++l)
+                        if (act[j][l]) {
+                            fx[j][l] = fma(m, A[j][l].hrx + B[j][l].hrx, fx[j][l]);
+                            fy[j][l] = fma(m, A[j][l].hry + B[j][l].hry, fy[j][l]);
+                        }
             }
         }
         if (GRAD) {

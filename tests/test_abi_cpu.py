@@ -69,7 +69,7 @@ def test_team_rule_is_the_same_in_library_and_oracle(cuda_solver_lib):
             cd = Dims(N=N, Ndyn=Ndyn).to_c()
             g = cuda_solver_lib.mpcb_team_groups(ctypes.byref(cd))
             assert g == OL.mpcl_team_groups(ctypes.byref(cd)), (N, Ndyn)
-            assert g == 0 or (g & (g - 1) == 0 and g <= 32 and g * N <= 352), (N, Ndyn, g)
+            assert g == 0 or (g & (g - 1) == 0 and g <= 32 and g * N <= 320), (N, Ndyn, g)
     assert cuda_solver_lib.mpcb_team_groups(ctypes.byref(Dims().to_c())) == 0
     assert cuda_solver_lib.mpcb_team_groups(ctypes.byref(Dims(Ndyn=40).to_c())) == 0
     assert cuda_solver_lib.mpcb_team_groups(ctypes.byref(Dims(N=40, Ndyn=160).to_c())) == 8

@@ -63,3 +63,25 @@ def test_panoc_amplifies_roundoff():
     Ub, _ = oracle.solve_batch(dims, RobotSpec(), cfg, P, U0 + 1e-14, threads=8)
     du = np.max(np.abs(Ua - Ub), axis=1)
     assert np.median(du) > 1e-10        # >= 4 orders of magnitude amplification
+
+
+def test_iteration_budget_is_the_out_of_time_status():
+    """cfg.max_inner_total restates the reference's wall-clock cap (mpc_fast.yaml:45) as a budget on
+    inner iterations: both oracles stop at the budget, report NotConvergedOutOfTime (2) exactly for
+    the instances that needed more, and are untouched when it is off or generous."""
+    from dyobav_mpcnwta_warehouse_b200 import Dims, RobotSpec, SolverSettings, instances
+    from oracle import oracle
+    import numpy as np
+    d = Dims()
+    P = instances.generate(d, 12, seed=3)
+    for laned in (False, True):
+        U0, S0 = oracle.solve_batch(d, RobotSpec(), SolverSettings(), P, None, threads=8, laned=laned)
+        U1, S1 = oracle.solve_batch(d, RobotSpec(), SolverSettings(max_inner_total=700), P, None, threads=8, laned=laned)
+        U2, S2 = oracle.solve_batch(d, RobotSpec(), SolverSettings(max_inner_total=10**6), P, None, threads=8, laned=laned)
+        np.testing.assert_array_equal(U0, U2)
+        np.testing.assert_array_equal(S0, S2)
+        need_more = S0[:, 6] > 700
+        assert need_more.any() and (~need_more).any()
+        assert (S1[need_more, 9] == 2).all() and (S1[need_more, 6] == 700).all()
+        np.testing.assert_array_equal(S1[~need_more], S0[~need_more])
+        np.testing.assert_array_equal(U1[~need_more], U0[~need_more])
