@@ -1,25 +1,42 @@
 #!/usr/bin/env python
 """bench.py — MPC solves/s of the batched PANOC/ALM solver (BASELINE.json metric).
 
-A "step" is one pass of the hot path over one batch: every rank solves
-`--scenarios` (default 8192) scenarios x 8 multi-start guesses = 65 536 solves at the
-reference's default dims (N=20, np=2778) — BASELINE.json configs[3], sharded so that
-8 GPUs together cover 65 536 scenarios x 8 starts (weak scaling: per-GPU work fixed).
+A "step" is one pass of the hot path over one batch of synthetic warehouse-shaped instances.
+
+  --workload warehouse_b65536x8 (default, BASELINE configs[3], the headline metric): every rank
+             solves 8192 scenarios x 8 multi-start guesses = 65 536 solves at the reference's
+             default dims (N=20, np=2778); 8 GPUs together cover 65 536 scenarios x 8 starts
+             (weak scaling).  `--scaling strong` fixes the TOTAL at 65 536 x 8 = 524 288 solves
+             (configs[3] in full) and splits it over the ranks; `--gpus 1 --scaling strong` is the
+             full-size single-GPU run.
+  --workload warehouse_b4096_ndyn40 (configs[2]): 4096 scenarios, 2 pedestrians x 20 SWTA modes
+  --workload dense_crowd_n40 (configs[4]): N=40, 160 ellipses, 16 384 scenarios (team kernel)
 
   value        solves/s, inputs already resident in HBM, CUDA-event timed, max over ranks
   e2e          same metric through BatchedSolver.run_batch with HOST (pinned) buffers:
                H2D of P and U0 and D2H of (u, cost, exit_status) inside the timed region
   roofline     the solve kernel against the FP64 pipe (this path is sequential small-state
-               recursion + reductions: neither HBM- nor tensor-bound)
-  cpu_baseline the CPU oracle port on this box's host cores, bounded sample
-  --impl reference   the same oracle port timed alone (the reference's own solver is
-               generated Rust/C that cannot be built without cargo/casadi)
+               recursion + reductions: neither HBM- nor tensor-bound); `achieved` is
+               the DENSE-EQUIVALENT algorithmic work (SURVEY §8(d) W_psi x evaluations counted by
+               the kernel) / time — exact culling skips most of it, so it is NOT pipe utilisation;
+               the measured pipe numbers of the committed ncu capture are reported next to it
+  solve_stats  exit-status histogram, iterations/s, share of the inner iterations spent after
+               |gamma fpr| < tolerance (the AKKT test keeps those solves going)
+  budgeted     a second value under an iteration budget that stands for the reference's 100 ms
+               wall-clock cap (mpc_fast.yaml:45): cfg.max_inner_total -> NotConvergedOutOfTime
+  latency      BASELINE configs[1]: 1000 single solves after 50 warm-ups through solver().run(p),
+               next to the CPU port's single-solve latency on the same instances
+  cpu_baseline the CPU oracle port on this box's host cores, bounded sample of the same scenarios
+  --impl reference   the same oracle port timed alone (the reference's own solver is generated
+               Rust/C that cannot be built without cargo/casadi: see `route_a_probe`)
 """
 from __future__ import annotations
 
 import argparse
+import importlib.util
 import json
 import os
+import shutil
 import subprocess
 import sys
 import threading
@@ -30,16 +47,35 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-# algorithmic work of one horizon evaluation at the default dims
-W_PSI_FLOP = {"default": 36.0e3}
-W_LBFGS_FLOP = 1.84e3
+HEADLINE = "warehouse_b65536x8"
+PER_GPU_SCENARIOS = {"warehouse_b65536x8": 8192, "warehouse_b4096_ndyn40": 4096, "dense_crowd_n40": 16384}
+CONFIG_OF = {"warehouse_b65536x8": "BASELINE configs[3]", "warehouse_b4096_ndyn40": "BASELINE configs[2]",
+             "dense_crowd_n40": "BASELINE configs[4]"}
+STATUS_NAMES = ("Converged", "NotConvergedIterations", "NotConvergedOutOfTime", "NotFiniteComputation")
 
 
 def w_psi(dims):
-    """SURVEY §8(d) per-unit figure, generalised over dims (same counting convention)."""
+    """SURVEY §8(d) per-unit figure (flop of one horizon evaluation), generalised over dims."""
     N = dims.N
     per_step = 70 + 9 + 8 * (2 * dims.Nother - 1) + 2 + 29 * dims.Nstc + 66 * dims.Ndyn
     return N * per_step + 25 * (N * (N + 1) // 2) + 10 * 2 * N + 2 * dims.n2
+
+
+def w_lbfgs(dims, mem=10):
+    """L-BFGS two-loop per iteration, 4 m n + 6 n."""
+    n = 2 * dims.N
+    return 4 * mem * n + 6 * n
+
+
+def route_a_probe():
+    """can the REAL OpEn solver be built on this box?  (It never could so far:
+    the reference arm then times the C port, labelled kind='port'.)"""
+    have = {m: importlib.util.find_spec(m) is not None for m in ("opengen", "casadi")}
+    have["cargo"] = shutil.which("cargo") is not None
+    have["rustc"] = shutil.which("rustc") is not None
+    have["baseline/_ref"] = os.path.isdir(os.path.join(ROOT, "baseline", "_ref"))
+    have["usable"] = bool(have["opengen"] and have["casadi"] and have["cargo"])
+    return have
 
 
 def hbm_roofline(algorithmic_bytes, seconds):
@@ -53,6 +89,15 @@ def hbm_roofline(algorithmic_bytes, seconds):
     ach = algorithmic_bytes / seconds / 1e9
     return {"achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": src,
             "note": "algorithmic bytes 8*(np/starts + 2*2N + 10) per solve; far from the bound by design"}
+
+
+def ncu_summary(workload):
+    """Measured pipe numbers of the committed ncu capture of this workload's kernel (profiles/)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_ncu_summary.json")) as fh:
+            return json.load(fh).get(workload)
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -98,8 +143,18 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def cpu_baseline(dims, robot, cfg, P, U0, starts, n_solves, threads):
-    """Time the oracle port on `n_solves` instances of the same workload with `threads` cores."""
+def make_inputs(wl, n_scenarios, rank=0):
+    """Rank `rank`'s scenarios of a workload: the same generator call in every arm, so that a CPU
+    sample P[:k] is a prefix of exactly what the GPU solves."""
+    from dyobav_mpcnwta_warehouse_b200 import instances
+    seed = wl.seed + 1000 * rank
+    P = instances.generate(wl.dims, n_scenarios, seed=seed, pedestrians=wl.pedestrians, modes=wl.modes)
+    U0 = instances.multistart_guesses(wl.dims, P, wl.starts, seed)
+    return P, U0
+
+
+def cpu_solve(dims, robot, cfg, P, U0, starts, n_solves, threads):
+    """Time the oracle port on the first `n_solves` instances with `threads` host threads."""
     from oracle import oracle
     n_p = max(1, n_solves // starts)
     t0 = time.perf_counter()
@@ -108,56 +163,93 @@ def cpu_baseline(dims, robot, cfg, P, U0, starts, n_solves, threads):
     return n_p * starts / dt, n_p * starts, dt, U, SC
 
 
+def histogram(status):
+    st = np.asarray(status).astype(np.int64)
+    return {STATUS_NAMES[i]: float((st == i).mean()) for i in range(4) if (st == i).any()}
+
+
+def launch_tail(ws):
+    """Launch profile of the last solve (workspace header, include/mpcb.h): when each warp ran out of
+    work.  Returns the time from the moment half of the solver warps were idle to the end of the
+    kernel, as a fraction of the kernel's duration."""
+    import torch
+    CT, WP, CB = 1024, 16, 4096
+    hdr = ws[CB:CB + CT * (1 + WP) * 8].view(torch.int64).cpu().numpy()
+    start = hdr[:CT]
+    fin = hdr[CT:].reshape(CT, WP)
+    fin = fin[fin > 0]
+    start = start[start > 0]
+    if fin.size == 0 or start.size == 0:
+        return None
+    t0, t1 = float(start.min()), float(fin.max())
+    half = float(np.sort(fin)[fin.size // 2])
+    return {"kernel_ms": (t1 - t0) / 1e6, "half_idle_to_end_ms": (t1 - half) / 1e6,
+            "tail_frac": (t1 - half) / max(1.0, t1 - t0), "warps": int(fin.size)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--scenarios", type=int, default=8192, help="scenarios per GPU (x8 starts)")
-    ap.add_argument("--starts", type=int, default=8)
-    ap.add_argument("--cpu-solves", type=int, default=0, help="CPU sample size (0: 24 per core)")
-    ap.add_argument("--latency-solves", type=int, default=24, help="single-solve latency sample (0: skip)")
+    ap.add_argument("--workload", default=HEADLINE, choices=sorted(PER_GPU_SCENARIOS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--scenarios", type=int, default=0, help="scenarios per GPU (0: the workload's own)")
+    ap.add_argument("--cpu-solves", type=int, default=0, help="CPU sample size (0: 64 per core, >= 512)")
+    ap.add_argument("--latency-solves", type=int, default=1000, help="single-solve latency sample (0: skip)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the short lines of the other workloads")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
-    from dyobav_mpcnwta_warehouse_b200 import Dims, RobotSpec, SolverSettings, instances
-    dims, robot, cfg = Dims(), RobotSpec(), SolverSettings()
-    starts = args.starts
+    from dyobav_mpcnwta_warehouse_b200 import RobotSpec, SolverSettings, instances
+    wl = instances.workload(args.workload)
+    dims, robot, cfg, starts = wl.dims, RobotSpec(), SolverSettings(), wl.starts
     cores = os.cpu_count() or 1
-    config = {"workload": "warehouse_b65536x8 (BASELINE configs[3]): N=20, np=2778, "
-                          f"{args.scenarios} scenarios x {starts} multi-start guesses per GPU",
-              "solves_per_gpu": args.scenarios * starts, "settings": "tol 1e-4, <=10 outer x <=500 inner, c0=10",
-              "l2": "inputs larger than L2 (P shard %.0f MB + staged copy)" % (args.scenarios * dims.np * 8 / 1e6)}
+    per_gpu = args.scenarios or PER_GPU_SCENARIOS[args.workload]
+    if args.scaling == "strong":
+        n_global = args.scenarios or wl.n_scenarios           # total fixed; split over the ranks
+    else:
+        n_global = per_gpu * world
+    config = {"workload": f"{wl.name} ({CONFIG_OF[wl.name]}): N={dims.N}, np={dims.np}, Ndyn={dims.Ndyn}, "
+                          f"{n_global} scenarios x {starts} multi-start guesses over {world} GPU(s)",
+              "solves_total": n_global * starts, "scaling": args.scaling,
+              "settings": "tol 1e-4, <=10 outer x <=500 inner, c0=10 (mpc_builder.py:187-195), no iteration budget",
+              "l2": "inputs larger than L2 (P shard %.0f MB + staged copy)" % (n_global / world * dims.np * 8 / 1e6)}
 
     # ---------------------------------------------------------------- reference arm
     if args.impl == "reference":
         if rank != 0:
             return
-        n_solves = args.cpu_solves or max(16, 8 * cores)
-        n_p = max(1, n_solves // starts)
-        P = instances.generate(dims, n_p, seed=instances.BASE_SEED + 4)
-        U0 = instances.multistart_guesses(dims, P, starts, instances.BASE_SEED + 4)
+        # the same scenarios as rank 0 of our arm: a prefix of its batch
+        total = args.cpu_solves or 2048
+        per_step = max(starts, -(-total // max(1, args.steps)))
+        n_p = max(1, per_step // starts)
+        P, U0 = make_inputs(wl, max(per_gpu, n_p * max(1, args.steps)), rank=0)
         for _ in range(args.warmup):
-            cpu_baseline(dims, robot, cfg, P, U0, starts, min(cores, n_p * starts), cores)
+            cpu_solve(dims, robot, cfg, P, U0, starts, min(cores, n_p) * starts, cores)
         t_tot, n_tot = 0.0, 0
-        for _ in range(args.steps):
-            v, n, dt, _, _ = cpu_baseline(dims, robot, cfg, P, U0, starts, n_p * starts, cores)
+        for s in range(args.steps):
+            lo = s * n_p
+            v, n, dt, _, _ = cpu_solve(dims, robot, cfg, P[lo:lo + n_p], U0[lo * starts:(lo + n_p) * starts],
+                                       starts, n_p * starts, cores)
             t_tot += dt
             n_tot += n
         val = n_tot / t_tot
         line = {"impl": "reference", "metric": "MPC solves/sec", "value": val, "unit": "solves/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak",
+                "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": args.scaling,
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "route_a_probe": route_a_probe(),
                 "cpu_baseline": {"value": val, "unit": "solves/s", "cores": cores, "kind": "port",
-                                 "sample": f"{n_p * starts} solves per step of the same workload "
-                                           "(oracle C port of OpEn PANOC/ALM, OpenMP over instances; the reference's "
-                                           "generated Rust solver cannot be built here)"},
+                                 "sample": f"{n_tot} solves in {args.steps} steps ({n_p * starts} per step), scenarios "
+                                           "drawn by the generator call of rank 0's batch; oracle C port of OpEn "
+                                           "PANOC/ALM (-O3 -march=x86-64-v3, OpenMP over instances, "
+                                           f"{cores} threads); the reference's generated Rust solver cannot be built here"},
                 "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -167,31 +259,15 @@ def main():
     import torch.distributed as dist
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm")
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
-        os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the one JSON line
+    os.environ.setdefault("NCCL_DEBUG", "WARN")       # keeps stdout to the one JSON line; overridable
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from dyobav_mpcnwta_warehouse_b200.solver import BatchedSolver
     from dyobav_mpcnwta_warehouse_b200.csrc import build as cbuild
+    from dyobav_mpcnwta_warehouse_b200 import sharding, _lib
     cbuild.build()
-
-    from dyobav_mpcnwta_warehouse_b200 import sharding
-    n_global = args.scenarios * world                     # weak scaling: 8192 scenarios per GPU
-    lo, hi = sharding.shard_range(n_global, rank, world)  # contiguous slice, all starts together
-    seed = instances.BASE_SEED + 4 + 1000 * rank          # each rank generates its own slice
-    P = instances.generate(dims, hi - lo, seed=seed)
-    U0 = instances.multistart_guesses(dims, P, starts, seed)
-    B = (hi - lo) * starts
-    solver = BatchedSolver(dims, robot, cfg, device=dev)
-    P_h = torch.from_numpy(P).pin_memory()
-    U0_h = torch.from_numpy(U0).pin_memory()
-    P_d, U0_d = P_h.to(dev), U0_h.to(dev)
-    out = solver.alloc_outputs(B)
-    u_h = torch.empty((B, dims.nu_total), dtype=torch.float64).pin_memory()
-    cost_h = torch.empty(B, dtype=torch.float64).pin_memory()
-    st_h = torch.empty(B, dtype=torch.int32).pin_memory()
     stream = torch.cuda.current_stream(dev)
 
     def barrier():
@@ -199,22 +275,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def step_resident():
-        solver.run_batch(P_d, U0_d, starts=starts, out=out)
-
-    def step_e2e():
-        # host buffers in, host buffers out; the only inter-GPU traffic of the whole job is
-        # the final gather of the best-of-starts solutions
-        Pd = P_h.to(dev, non_blocking=True)
-        Ud = U0_h.to(dev, non_blocking=True)
-        o = solver.run_batch(Pd, Ud, starts=starts, out=out)
-        bc, bu, bs, _ = sharding.best_of_starts(o["cost"], o["u"], o["exit_status"], starts)
-        sharding.gather_results({"u": bu, "cost": bc, "exit_status": bs}, n_global)
-        u_h.copy_(o["u"], non_blocking=True)
-        cost_h.copy_(o["cost"], non_blocking=True)
-        st_h.copy_(o["exit_status"], non_blocking=True)
-
     def timed(fn, steps):
+        """CUDA-event time of `steps` calls, barrier + synchronize on both sides; (max over ranks, own)."""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record(stream)
@@ -222,93 +284,230 @@ def main():
             fn()
         e1.record(stream)
         barrier()
-        ms = e0.elapsed_time(e1)
+        own = e0.elapsed_time(e1)
+        ms = own
         if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            t = torch.tensor([own], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms
+        return ms, own
 
-    for _ in range(args.warmup):
-        step_resident()
-    with ClockSampler(local_rank) as clk:
-        ms = timed(step_resident, args.steps)
-    # the dominant kernel alone, on the launching stream (roofline): K3 staging is
-    # ~0.1 % of a step, so the step time is the solve kernel's time to that precision
-    ev = out["evals"].to(torch.float64).sum(0)
-    n_inner = out["n_inner"].to(torch.float64).sum()
-    wps = w_psi(dims)
-    flop_per_launch = float(ev[0]) * wps + float(ev[1]) * 3 * wps + float(n_inner) * W_LBFGS_FLOP
-    ms_e2e = timed(step_e2e, args.steps)
-    total_solves = B * world
-    value = total_solves * args.steps / (ms / 1e3)
-    e2e = total_solves * args.steps / (ms_e2e / 1e3)
+    def measure(wl, n_global, steps, warmup, full, warm_scenarios=0):
+        """One workload on this rank's shard.  `full`: also the e2e leg.  `warm_scenarios` > 0: the
+        warm-up passes run on that many scenarios only (the short lines of the other workloads)."""
+        dims, starts = wl.dims, wl.starts
+        lo, hi = sharding.shard_range(n_global, rank, world)  # contiguous slice, all starts together
+        P, U0 = make_inputs(wl, hi - lo, rank=rank)           # each rank generates its own slice
+        B = (hi - lo) * starts
+        solver = BatchedSolver(dims, robot, cfg, device=dev)
+        P_h = torch.from_numpy(P).pin_memory()
+        U0_h = torch.from_numpy(U0).pin_memory()
+        P_d, U0_d = P_h.to(dev), U0_h.to(dev)
+        out = solver.alloc_outputs(B)
 
-    status = out["exit_status"]
-    stats = {"converged_frac": float((status == 0).double().mean()),
-             "mean_inner_iters": float(out["n_inner"].double().mean()),
-             "mean_cost_evals": float(out["evals"][:, 0].double().mean()),
-             "mean_costgrad_evals": float(out["evals"][:, 1].double().mean())}
+        def step_resident():
+            solver.run_batch(P_d, U0_d, starts=starts, out=out)
 
-    if rank != 0:
+        for _ in range(warmup):
+            if warm_scenarios and warm_scenarios < hi - lo:
+                solver.run_batch(P_d[:warm_scenarios], U0_d[:warm_scenarios * starts], starts=starts)
+            else:
+                step_resident()
+        with ClockSampler(local_rank) as clk:
+            ms, own_ms = timed(step_resident, steps)
+        tail = launch_tail(solver._ws)
+        ev = out["evals"][:, :2].to(torch.float64).sum(0)
+        n_inner = float(out["n_inner"].to(torch.float64).sum())
+        n_small = float(out["evals"][:, 2].to(torch.float64).sum())
+        wps, wlb = w_psi(dims), w_lbfgs(dims, cfg.lbfgs_mem)
+        flop = float(ev[0]) * wps + float(ev[1]) * 3 * wps + n_inner * wlb
+        status = out["exit_status"].cpu().numpy()
+        # per-rank record (N > 1: shows where the max over ranks comes from)
+        rec = torch.tensor([own_ms / steps, n_inner / B, float((status == 0).mean()),
+                            tail["tail_frac"] if tail else -1.0], dtype=torch.float64, device=dev)
         if world > 1:
-            dist.destroy_process_group()
-        return
+            allrec = [torch.zeros_like(rec) for _ in range(world)]
+            dist.all_gather(allrec, rec)
+            glob = torch.tensor([flop, float(B), n_inner, n_small], dtype=torch.float64, device=dev)
+            dist.all_reduce(glob)
+            flop_all, B_all, inner_all, small_all = [float(x) for x in glob.tolist()]
+        else:
+            allrec = [rec]
+            flop_all, B_all, inner_all, small_all = flop, float(B), n_inner, n_small
+        res = {"ms": ms, "steps": steps, "B_all": B_all, "B": B, "value": B_all * steps / (ms / 1e3),
+               "flop_all": flop_all, "dims": dims, "wps": wps, "wlb": wlb,
+               "stats": {"exit_status_histogram": histogram(status),
+                         "converged_frac": float((status == 0).mean()),
+                         "mean_inner_iters": inner_all / B_all,
+                         "inner_iters_per_s": inner_all * steps / (ms / 1e3),
+                         "frac_iters_after_fpr_below_tol": small_all / max(1.0, inner_all),
+                         "mean_cost_evals": float(out["evals"][:, 0].double().mean()),
+                         "mean_costgrad_evals": float(out["evals"][:, 1].double().mean()),
+                         "note": "rank 0's shard for the histogram and evaluation means; iteration figures over all ranks. "
+                                 "frac_iters_after_fpr_below_tol: inner iterations that began with |gamma fpr| < 1e-4 "
+                                 "but failed the AKKT test |fpr| < eps_nu (the solve keeps iterating)"},
+               "per_rank": [{"rank": i, "ms_per_step": float(r[0]), "mean_inner_iters": float(r[1]),
+                             "converged_frac": float(r[2]), "launch_tail_frac": float(r[3])}
+                            for i, r in enumerate(x.tolist() for x in allrec)],
+               "launch_tail": tail, "clocks": clk.summary(), "P": P, "U0": U0, "solver": solver}
+        if not full:
+            return res
+        # ---- e2e: host buffers in, host buffers out; the only inter-GPU traffic of the whole job
+        #      is the final gather of the best-of-starts solutions
+        u_h = torch.empty((B, dims.nu_total), dtype=torch.float64).pin_memory()
+        cost_h = torch.empty(B, dtype=torch.float64).pin_memory()
+        st_h = torch.empty(B, dtype=torch.int32).pin_memory()
 
-    fp64_nominal = 148 * 64 * 2 * 1.965e9 / 1e12  # 64 FP64 FMA/clk/SM at max clock
-    from dyobav_mpcnwta_warehouse_b200 import _lib
-    try:
-        fp64_peak, peak_src = _lib.fp64_peak_tflops(), "measured live: 8 independent DFMA chains/thread (mpcb_fp64_peak_tflops)"
-    except Exception as exc:                      # never fall back silently
-        raise RuntimeError(f"FP64 peak probe failed: {exc}")
-    kernel_s = ms / 1e3 / args.steps
-    achieved = flop_per_launch / kernel_s / 1e12
-    line = {
-        "metric": "MPC solves/sec", "value": value, "unit": "solves/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": config,
-        "e2e": {"value": e2e, "unit": "solves/s",
-                "h2d_bytes_per_step": int(P_h.numel() * 8 + U0_h.numel() * 8),
-                "d2h_bytes_per_step": int(u_h.numel() * 8 + cost_h.numel() * 8 + st_h.numel() * 4)},
-        "gpu_launches": 2 * args.steps,
-        "clocks": clk.summary(),
-        "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                     "frac": achieved / fp64_peak,
-                     # ncu dram__bytes_read+write of this kernel: 43 384 064 B for 16 384 solves
-                     # (profiles/r1_traffic_metrics.csv) = 2 648 B per solve,
-                     # scaled to this launch
-                     "traffic": 2648.0 * B,
-                     "peak_source": peak_src, "peak_nominal": fp64_nominal,
-                     "note": "MEASURED_PEAKS.json holds no FP64 figure, so the FMA pipe is probed in this run "
-                             "(nominal 148 SM x 64 FMA/clk x 1.965 GHz = 37.2). achieved = SURVEY 8(d) work "
-                             f"(W_psi={wps} flop, grad=3x, L-BFGS {W_LBFGS_FLOP:.0f}/iter) x evaluations "
-                             "counted by the kernel / CUDA-event time",
-                     "hbm": hbm_roofline((B * 8 * (dims.np / starts + 2 * dims.nu_total + 10)), kernel_s)},
-        "solve_stats": stats,
-    }
-    if args.latency_solves > 0:
-        # BASELINE configs[1]: one solve per call through the drop-in `solver().run(p)`, host lists
+        def step_e2e():
+            Pd = P_h.to(dev, non_blocking=True)
+            Ud = U0_h.to(dev, non_blocking=True)
+            o = solver.run_batch(Pd, Ud, starts=starts, out=out)
+            bc, bu, bs, _ = sharding.best_of_starts(o["cost"], o["u"], o["exit_status"], starts)
+            sharding.gather_results({"u": bu, "cost": bc, "exit_status": bs}, n_global)
+            u_h.copy_(o["u"], non_blocking=True)
+            cost_h.copy_(o["cost"], non_blocking=True)
+            st_h.copy_(o["exit_status"], non_blocking=True)
+
+        ms_e2e, _ = timed(step_e2e, steps)
+        res["e2e"] = {"value": B_all * steps / (ms_e2e / 1e3), "unit": "solves/s",
+                      "h2d_bytes_per_step": int(P_h.numel() * 8 + U0_h.numel() * 8),
+                      "d2h_bytes_per_step": int(u_h.numel() * 8 + cost_h.numel() * 8 + st_h.numel() * 4)}
+        res["P_d"], res["U0_d"], res["out"] = P_d, U0_d, out
+        return res
+
+    def roofline_of(res, fp64_peak, fp64_nominal, peak_src, workload):
+        kernel_s = res["ms"] / 1e3 / res["steps"]
+        achieved = res["flop_all"] / world / kernel_s / 1e12          # per GPU (max-over-ranks time)
+        d = res["dims"]
+        r = {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+             "frac": achieved / fp64_peak, "frac_nominal": achieved / fp64_nominal, "peak_nominal": fp64_nominal,
+             "what": "effective (dense-equivalent) TFLOP/s per GPU: SURVEY 8(d) algorithmic work "
+                     f"(W_psi={res['wps']} flop, gradient=3x, L-BFGS {res['wlb']}/iteration) x the evaluations the kernel "
+                     "counted / CUDA-event time.  Exact culling skips most of that work, so this is NOT pipe utilisation",
+             "traffic": None,
+             "peak_source": peak_src,
+             "hbm": hbm_roofline(res["B"] * 8 * (d.np / wl_starts(workload) + 2 * d.nu_total + 10), kernel_s)}
+        ncu = ncu_summary(workload)
+        if ncu:
+            r["pipe_fp64_active"] = ncu.get("pipe_fp64_active_pct")
+            r["issue_active"] = ncu.get("issue_active_pct")
+            r["traffic"] = ncu.get("dram_bytes_per_launch")
+            r["ncu_capture"] = ncu.get("file")
+        return r
+
+    def wl_starts(name):
+        return instances.workload(name).starts
+
+    res = measure(wl, n_global, args.steps, args.warmup, full=True)
+    if rank == 0:
+        fp64_nominal = 148 * 64 * 2 * 1.965e9 / 1e12  # 64 FP64 FMA/clk/SM at max clock
+        try:
+            fp64_peak = _lib.fp64_peak_tflops()
+            peak_src = ("measured live: 8 independent DFMA chains/thread (mpcb_fp64_peak_tflops); MEASURED_PEAKS.json "
+                        "holds no FP64 figure; nominal 148 SM x 64 FMA/clk x 1.965 GHz = 37.2")
+        except Exception as exc:                      # never fall back silently
+            raise RuntimeError(f"FP64 peak probe failed: {exc}")
+    line = None
+    if rank == 0:
+        line = {
+            "metric": "MPC solves/sec", "value": res["value"], "unit": "solves/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms"] / args.steps,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config, "e2e": res["e2e"],
+            "gpu_launches": 2 * args.steps, "clocks": res["clocks"],
+            "roofline": roofline_of(res, fp64_peak, fp64_nominal, peak_src, wl.name),
+            "solve_stats": res["stats"], "per_rank": res["per_rank"], "launch_tail": res["launch_tail"],
+            "route_a_probe": route_a_probe(),
+        }
+
+    # ---- a second value under an iteration budget standing for the reference's 100 ms cap.  The
+    #      budget is 100 ms worth of the CPU port's own inner iterations (measured below when the CPU
+    #      leg runs; 690 = 0.1 s x 6.9k iterations/s/core as measured in round 1 otherwise).
+    cpu_info = None
+    if rank == 0 and not args.no_cpu:
+        n_cpu = args.cpu_solves or max(512, 64 * cores)
+        v, n, dt, _, SC = cpu_solve(dims, robot, cfg, res["P"], res["U0"], starts, n_cpu, cores)
+        it_per_core_s = float(SC[:, 6].sum()) / dt / min(cores, n)
+        cpu_info = {"value": v, "unit": "solves/s", "cores": cores, "kind": "port",
+                    "sample": f"first {n} solves of rank 0's batch, {dt:.1f} s wall, oracle C port "
+                              "(-O3 -march=x86-64-v3, OpenMP over instances)",
+                    "inner_iters_per_core_s": it_per_core_s,
+                    "exit_status_histogram": histogram(SC[:, 9]),
+                    "mean_inner_iters": float(SC[:, 6].mean())}
+        line["cpu_baseline"] = cpu_info
+    budget = 690
+    if cpu_info:
+        budget = max(1, int(round(0.1 * cpu_info["inner_iters_per_core_s"])))
+    if world > 1:
+        b = torch.tensor([budget], dtype=torch.int64, device=dev)
+        dist.broadcast(b, 0)
+        budget = int(b.item())
+    if args.workload == HEADLINE:
+        from dyobav_mpcnwta_warehouse_b200.problem import SolverSettings as SS
+        bsolver = BatchedSolver(dims, robot, SS(max_inner_total=budget), device=dev)
+        bout = bsolver.alloc_outputs(res["B"])
+        fnb = lambda: bsolver.run_batch(res["P_d"], res["U0_d"], starts=starts, out=bout)  # noqa: E731
+        fnb()
+        ms_b, _ = timed(fnb, args.steps)
+        if rank == 0:
+            stb = bout["exit_status"].cpu().numpy()
+            line["budgeted"] = {"max_inner_total": budget, "value": res["B_all"] * args.steps / (ms_b / 1e3),
+                                "unit": "solves/s", "exit_status_histogram": histogram(stb),
+                                "mean_inner_iters": float(bout["n_inner"].double().mean()),
+                                "what": "same batch with cfg.max_inner_total = 100 ms worth of the CPU port's inner "
+                                        "iterations on one host core: the batch analogue of max_solver_time "
+                                        "(mpc_fast.yaml:45); exhausted -> NotConvergedOutOfTime, as the reference reports"}
+
+    # ---- BASELINE configs[1]: single solves through the drop-in `solver().run(p)`, host lists
+    if rank == 0 and args.latency_solves > 0 and args.workload == HEADLINE:
         from dyobav_mpcnwta_warehouse_b200.solver import solver as make_solver
+        from oracle import oracle
         s1 = make_solver(dims, robot, cfg)
+        P = res["P"]
+        rows = [P[i % P.shape[0]].tolist() for i in range(50 + args.latency_solves)]
+        for i in range(50):
+            s1.run(rows[i])
         wall, dev_ms = [], []
-        for i in range(min(args.latency_solves, P.shape[0])):
-            row = P[i].tolist()
+        for i in range(50, 50 + args.latency_solves):
             t0 = time.perf_counter()
-            r = s1.run(row)
+            r = s1.run(rows[i])
             wall.append(1e3 * (time.perf_counter() - t0))
             dev_ms.append(r.solve_time_ms)
+        ncpu = min(48, args.latency_solves)
+        cpu_ms = []
+        for i in range(50, 50 + ncpu):
+            t0 = time.perf_counter()
+            oracle.solve(dims, robot, cfg, np.asarray(rows[i]))
+            cpu_ms.append(1e3 * (time.perf_counter() - t0))
         line["latency"] = {"p50_ms": float(np.percentile(wall, 50)), "p95_ms": float(np.percentile(wall, 95)),
-                           "p50_device_ms": float(np.percentile(dev_ms, 50)), "solves": len(wall),
-                           "what": "wall clock of solver().run(p) incl. H2D/D2H, one instance per call, "
-                                   "reference settings (no wall-clock cap)"}
-    if not args.no_cpu and world >= 1:
-        n_cpu = args.cpu_solves or max(16, 24 * cores)
-        v, n, dt, _, _ = cpu_baseline(dims, robot, cfg, P, U0, starts, n_cpu, cores)
-        line["cpu_baseline"] = {"value": v, "unit": "solves/s", "cores": cores, "kind": "port",
-                                "sample": f"first {n} solves of rank 0's batch, {dt:.1f} s wall, "
-                                          "oracle C port (OpenMP over instances)"}
-    print(json.dumps(line))
+                           "p50_device_ms": float(np.percentile(dev_ms, 50)), "solves": len(wall), "warmup": 50,
+                           "gpu_p50_ms_same_instances_as_cpu": float(np.percentile(wall[:ncpu], 50)),
+                           "cpu_port_p50_ms": float(np.percentile(cpu_ms, 50)),
+                           "cpu_port_p95_ms": float(np.percentile(cpu_ms, 95)), "cpu_solves": ncpu,
+                           "what": "wall clock of solver().run(p) incl. H2D/D2H, one instance per call (one warp on one "
+                                   "SM), reference settings, no wall-clock cap; CPU port: one thread, same instances"}
+
+    # ---- the other BASELINE workloads, briefly (full lines: --workload ...)
+    if args.workload == HEADLINE and not args.no_others and args.scaling == "weak":
+        others = {}
+        for name in ("warehouse_b4096_ndyn40", "dense_crowd_n40"):
+            w2 = instances.workload(name)
+            r2 = measure(w2, PER_GPU_SCENARIOS[name] * world, 1, 3, full=False, warm_scenarios=296)
+            if rank == 0:
+                rf = roofline_of(r2, fp64_peak, fp64_nominal, peak_src, name)
+                others[name] = {"config": CONFIG_OF[name], "value": r2["value"], "unit": "solves/s",
+                                "solves": int(r2["B_all"]), "steps": 1, "warmup": "3 passes over 296 scenarios",
+                                "ms_per_step": r2["ms"],
+                                "roofline_frac": rf["frac"], "roofline_achieved_tflops": rf["achieved"],
+                                "pipe_fp64_active": rf.get("pipe_fp64_active"),
+                                "converged_frac": r2["stats"]["converged_frac"],
+                                "mean_inner_iters": r2["stats"]["mean_inner_iters"]}
+            del r2
+            torch.cuda.empty_cache()
+        if rank == 0:
+            line["other_workloads"] = others
+    if rank == 0:
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

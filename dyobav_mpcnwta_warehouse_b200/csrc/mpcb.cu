@@ -444,6 +444,11 @@ __global__ void __launch_bounds__(qthreads(FIXED), MPCB_MIN_CTAS) solve_kernel_q
     const int warp = threadIdx.x >> 5;
     asm volatile("" : "+r"(lane));   // keep the lane id in a register (S2R is slow to re-read)
     double* lb = lb_all + (size_t)warp * P.lb_doubles;
+    if (threadIdx.x == 0 && P.prof) {
+        unsigned long long tns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
+        P.prof[blockIdx.x & (MPCB_WS_PROF_CTAS - 1)] = tns;
+    }
     solve_worker<SPL, 1, FIXED>(P, nullptr, staged, counter, lb, 0, lane, io);
 }
 
@@ -463,6 +468,11 @@ __global__ void __launch_bounds__(TEAM_THREADS, MPCB_TEAM_CTAS) solve_kernel_tea
     if (threadIdx.x < TEAM_NS) {
         TeamShared* Ts = reinterpret_cast<TeamShared*>(base + (size_t)threadIdx.x * sstride + P.lb_doubles);
         Ts->req = 0; Ts->done = 0; Ts->exit_ = 0;
+    }
+    if (threadIdx.x == 0 && P.prof) {
+        unsigned long long tns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
+        P.prof[blockIdx.x & (MPCB_WS_PROF_CTAS - 1)] = tns;
     }
     __syncthreads();
     if (warp < TEAM_NS) {
@@ -573,7 +583,11 @@ int env_int(const char* name, int dflt)
     return v && *v ? atoi(v) : dflt;
 }
 
-constexpr size_t WS_HEADER = 4096;  // bytes reserved for the work-queue counters (one per CTA)
+constexpr size_t WS_COUNTERS = MPCB_WS_COUNTER_BYTES;   // work-queue counters (one per CTA)
+// launch profile of the last solve: start time per CTA, finish time per (CTA, warp), globaltimer ns
+constexpr size_t WS_PROF = (size_t)MPCB_WS_PROF_CTAS * (1 + MPCB_WS_PROF_WARPS) * 8;
+constexpr size_t WS_HEADER = WS_COUNTERS + WS_PROF;
+static_assert(WS_HEADER == MPCB_WS_HEADER_BYTES, "include/mpcb.h documents the workspace header");
 
 struct Plan {
     KParams P;
@@ -684,7 +698,7 @@ int stage(const Plan& pl, const double* p, void* workspace, size_t ws_bytes, cud
     if ((reinterpret_cast<uintptr_t>(workspace) & 15) || (reinterpret_cast<uintptr_t>(p) & 7)) return MPCB_E_ALIGN;
     int* counter = reinterpret_cast<int*>(workspace);
     double* staged = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + WS_HEADER);
-    CUDA_TRY(cudaMemsetAsync(counter, 0, WS_HEADER, st));
+    CUDA_TRY(cudaMemsetAsync(counter, 0, WS_HEADER, st));   // counters and launch profile
     const int grid = pl.P.n_p < 148 * 16 ? pl.P.n_p : 148 * 16;
     stage_kernel<<<grid, 128, 0, st>>>(pl.P, p, staged);
     CUDA_TRY(cudaGetLastError());
@@ -797,6 +811,7 @@ int32_t mpcb_solve_f64(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solve
     rc = stage(pl, p, workspace, ws_bytes, st, &staged, &counter);
     if (rc) return rc;
     SolveIO io{u0, y0, c0, u_out, cost, exit_status, n_outer, n_inner, fpr, f1_infeas, f2_norm, penalty, y_out, evals};
+    pl.P.prof = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(workspace) + WS_COUNTERS);
     const int threads = pl.P.warps * 32;
     const int ngroups = (pl.P.B + pl.P.warps - 1) / pl.P.warps;
     int dev = 0, sms = 0;
@@ -825,7 +840,7 @@ int32_t mpcb_solve_f64(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solve
         if (env_int("MPCB_CTAS_PER_SM", 0) > 0) per_sm = env_int("MPCB_CTAS_PER_SM", 0);           \
         int grid = sms * per_sm;                                                                   \
         if (grid > ngroups) grid = ngroups;                                                        \
-        if (grid > (int)(WS_HEADER / sizeof(int))) grid = (int)(WS_HEADER / sizeof(int));          \
+        if (grid > (int)(WS_COUNTERS / sizeof(int))) grid = (int)(WS_COUNTERS / sizeof(int));      \
         solve_kernel_queue<SPL, MD><<<grid, threads, pl.smem_bytes, st>>>(pl.P, staged, io, counter); \
     } while (0)
 #define LAUNCH_TEAM(SPL, MD)                                                                       \
@@ -838,7 +853,7 @@ int32_t mpcb_solve_f64(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solve
         if (per_sm < 1) per_sm = 1;                                                                \
         int grid = sms * per_sm;                                                                   \
         if (grid > (pl.P.B + TEAM_NS - 1) / TEAM_NS) grid = (pl.P.B + TEAM_NS - 1) / TEAM_NS;       \
-        if (grid > (int)(WS_HEADER / sizeof(int))) grid = (int)(WS_HEADER / sizeof(int));          \
+        if (grid > (int)(WS_COUNTERS / sizeof(int))) grid = (int)(WS_COUNTERS / sizeof(int));      \
         solve_kernel_team<SPL, MD><<<grid, TEAM_THREADS, pl.smem_bytes, st>>>(pl.P, staged, io, counter); \
     } while (0)
     if (pl.team) {
@@ -894,12 +909,12 @@ int32_t mpcb_solve_one_host(const mpcb_dims* d, const mpcb_robot* r, const mpcb_
     mpcb_workspace_bytes(d, 1, 1, &ws);
     // one arena, mirrored on the device and in pinned host memory; every block starts on a
     // 256-byte boundary (u0 / u_out feed double2 loads and stores: any np, odd ones included):
-    //   inputs  p | u0 | y0 | c0     outputs  u | y | scalars(5 doubles) | ints(5)     workspace
+    //   inputs  p | u0 | y0 | c0     outputs  u | y | scalars(5 doubles) | ints(7)     workspace
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t o_p = 0, o_u0 = up(o_p + (size_t)L.np * 8), o_y0 = up(o_u0 + (size_t)n * 8),
                  o_c0 = up(o_y0 + (size_t)n * 8), o_in_end = up(o_c0 + 8);
     const size_t o_u = o_in_end, o_y = up(o_u + (size_t)n * 8), o_sc = up(o_y + (size_t)n * 8),
-                 o_i = up(o_sc + 5 * 8), o_out_end = up(o_i + 5 * 4), o_ws = o_out_end;
+                 o_i = up(o_sc + 5 * 8), o_out_end = up(o_i + 7 * 4), o_ws = o_out_end;
     // per-thread cached context: the single-solve path is called once per control period, so
     // allocation must not be on it
     static thread_local OneHostCtx t;

@@ -78,7 +78,9 @@ struct KParams {
     int lb_doubles;      // per-warp L-BFGS scratch (doubles)
     int cull;            // 1: skip provably-zero obstacle terms
     int budget;          // > 0: cap on the inner iterations of one solve (cfg->max_inner_total)
+    unsigned long long* prof;   // launch profile in the workspace header (nullable): [CTAS] start, [CTAS][WARPS] finish
 };
+#include "../../include/mpcb.h"     // MPCB_WS_PROF_CTAS / MPCB_WS_PROF_WARPS
 
 // One definition of the staged-block layout, usable at compile time (default dims are
 // constant-folded into the kernel) and at run time (any dims).
@@ -185,6 +187,11 @@ struct LayV {
 //     fx_k = fma(c F2_i, a.hrx + b.hrx, fx_k) for every step k (both slots added first).
 #ifndef MPCB_TEAM_WARPS
 #define MPCB_TEAM_WARPS 12
+#endif
+// which compiled-in dimension sets of the one-warp kernel use the position-based (block bounding
+// box) culling of the ellipses instead of the anchor-based margins
+#ifndef MPCB_BOX_CULL
+#define MPCB_BOX_CULL(FIXED) ((FIXED) != 1)
 #endif
 #ifndef MPCB_TEAM_SOLVERS
 #define MPCB_TEAM_SOLVERS 2
@@ -818,14 +825,64 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
         const double* etb = S + L.o_et();
         const float* me0b = MG + L.f_e0();
         const float* metb = MG + L.f_et();
+        // Position-based culling (BOX): the bounding box of the robot's positions over a block of 8
+        // steps against the bounding boxes of the ellipses of that block (staged by K3).  Unlike the
+        // anchor-based margins it keeps culling when the robot lags behind its reference.  Exact in
+        // the same sense: a skipped term is provably zero.
+        constexpr bool BOX = !TEAM && MPCB_BOX_CULL(FIXED);
+        float rlx[SPL], rhx[SPL], rly[SPL], rhy[SPL];
+        if constexpr (BOX) {
+            const float PINF = __int_as_float(0x7f800000);
+            const bool nocull = !(dmax < PINF);          // culling off, or a non-finite state
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) {
+                rlx[j] = act[j] ? __double2float_rd(X[j]) : PINF; rhx[j] = act[j] ? __double2float_ru(X[j]) : -PINF;
+                rly[j] = act[j] ? __double2float_rd(Y[j]) : PINF; rhy[j] = act[j] ? __double2float_ru(Y[j]) : -PINF;
+#pragma unroll
+                for (int m = 1; m < 8; m <<= 1) {
+                    rlx[j] = fminf(rlx[j], __shfl_xor_sync(FULL, rlx[j], m)); rhx[j] = fmaxf(rhx[j], __shfl_xor_sync(FULL, rhx[j], m));
+                    rly[j] = fminf(rly[j], __shfl_xor_sync(FULL, rly[j], m)); rhy[j] = fmaxf(rhy[j], __shfl_xor_sync(FULL, rhy[j], m));
+                }
+                if (nocull) { rlx[j] = -PINF; rhx[j] = PINF; rly[j] = -PINF; rhy[j] = PINF; }
+            }
+        }
 #pragma unroll 1
         for (int base = 0; base < L.Ndyn(); base += 32) {
             const int it = base + lane;
-            // team mode: only the ellipses a worker flagged (a raw hinge somewhere) are redone here
-            unsigned mk = TEAM ? T->hit[base >> 5]
-                               : __ballot_sync(FULL, it < L.Ndyn() && !(IM_E[it < L.Ndyn() ? it : 0] > dmax));
+            unsigned my0[SPL], my1[SPL];   // BOX: ellipses whose t = 0 / t = k+1 box meets the box of this lane's block
+            unsigned mk;
+            if constexpr (TEAM) {
+                // team mode: only the ellipses a worker flagged (a raw hinge somewhere) are redone here
+                mk = T->hit[base >> 5];
+            } else if constexpr (BOX) {
+                const bool valid = it < L.Ndyn();
+                const int o = valid ? it : 0;
+                const int NB = (N + 7) >> 3;
+                const float4 q0 = reinterpret_cast<const float4*>(MG + L.f_bx0())[o];
+                const float4* q1p = reinterpret_cast<const float4*>(MG + L.f_bx1()) + o * NB;
+                mk = 0u;
+#pragma unroll
+                for (int j = 0; j < SPL; ++j) { my0[j] = 0u; my1[j] = 0u; }
+#pragma unroll 1
+                for (int b = 0; b < NB; ++b) {
+                    const int ln = (8 * b) & 31;
+                    const bool hi = SPL > 1 && 8 * b >= 32;
+                    const float bl = __shfl_sync(FULL, hi ? rlx[SPL - 1] : rlx[0], ln), bh = __shfl_sync(FULL, hi ? rhx[SPL - 1] : rhx[0], ln);
+                    const float cl = __shfl_sync(FULL, hi ? rly[SPL - 1] : rly[0], ln), ch = __shfl_sync(FULL, hi ? rhy[SPL - 1] : rhy[0], ln);
+                    const float4 q1 = q1p[b];
+                    const unsigned m0 = __ballot_sync(FULL, valid && !(bl > q0.y || bh < q0.x || cl > q0.w || ch < q0.z));
+                    const unsigned m1 = __ballot_sync(FULL, valid && !(bl > q1.y || bh < q1.x || cl > q1.w || ch < q1.z));
+#pragma unroll
+                    for (int j = 0; j < SPL; ++j)
+                        if ((kk[j] >> 3) == b) { my0[j] = m0; my1[j] = m1; }
+                    mk |= m0 | m1;
+                }
+            } else {
+                mk = __ballot_sync(FULL, it < L.Ndyn() && !(IM_E[it < L.Ndyn() ? it : 0] > dmax));
+            }
             while (mk) {
-                const int i = base + __ffs(mk) - 1;
+                const int bit = __ffs(mk) - 1;
+                const int i = base + bit;
                 mk &= mk - 1;
                 EllT a[SPL], b[SPL];
                 double hl = 0.0;
@@ -852,14 +909,17 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
                     for (int j = 0; j < SPL; ++j) {
                         const int k = act[j] ? kk[j] : N - 1;
                         a[j].hr = 0.0; b[j].hr = 0.0; a[j].hrx = 0.0; a[j].hry = 0.0; b[j].hrx = 0.0; b[j].hry = 0.0;
-                        if (!(me0b[i * N + k] > Df[j])) {          // t = 0 slot (one ellipse for all steps)
+                        bool p0, p1;
+                        if constexpr (BOX) { p0 = (my0[j] >> bit) & 1u; p1 = (my1[j] >> bit) & 1u; }
+                        else { p0 = !(me0b[i * N + k] > Df[j]); p1 = !(metb[i * N + k] > Df[j]); }
+                        if (p0) {                                  // t = 0 slot (one ellipse for all steps)
                             ellipse_terms(GRAD, e0 + i, L.Ndyn(), X[j], Y[j], a[j]);
                             if constexpr (!TEAM) {
                                 cstj[j] += a[j].cost;
                                 if (GRAD) { gx[j] += a[j].gx; gy[j] += a[j].gy; }
                             }
                         }
-                        if (!(metb[i * N + k] > Df[j])) {          // t = k+1 slot
+                        if (p1) {                                  // t = k+1 slot
                             ellipse_terms(GRAD, etb + k + i * N, L.Ndyn() * N, X[j], Y[j], b[j]);
                             if constexpr (!TEAM) {
                                 cstj[j] += b[j].cost;

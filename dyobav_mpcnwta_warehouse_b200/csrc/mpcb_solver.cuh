@@ -69,7 +69,7 @@ struct ColdState {
     double akkt_tol;
     double dy, dy_plus, f2n, f2n_plus, last_fpr, fcost;
     int alm_iter, n_outer, inner_total, outer, inner, status, n_cost, n_grad;
-    int failed, qscan, pad[2];     // sizeof == 112: keeps the scratch a whole number of double2
+    int failed, qscan, n_small, pad;   // sizeof == 112: keeps the scratch a whole number of double2
 };
 // doubles of per-warp scratch after the L-BFGS rows: y, y+ (2N each), the parked solver vectors
 // (7 x (v, w) per horizon step), the parked PANOC scalars and the cold state
@@ -285,13 +285,21 @@ L_fetch:
                 break;
             }
         }
-        if (sc < 0) return;
+        if (sc < 0) {
+            // launch profile: when this warp ran out of work (globaltimer, ns)
+            if (lane == 0 && P.prof) {
+                unsigned long long tns;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
+                P.prof[MPCB_WS_PROF_CTAS + ((blockIdx.x * MPCB_WS_PROF_WARPS + (threadIdx.x >> 5)) & (MPCB_WS_PROF_CTAS * MPCB_WS_PROF_WARPS - 1))] = tns;
+            }
+            return;
+        }
         S = staged + (size_t)sc * LV.total();
         // opaque from here on: under register pressure the compiler would otherwise re-derive the
         // pointer (an integer division) inside the evaluation instead of keeping it
         asm volatile("" : "+l"(S));
     }
-    CS->n_cost = 0; CS->n_grad = 0;
+    CS->n_cost = 0; CS->n_grad = 0; CS->n_small = 0;
     MPCB_FORJ {
         const int k = lane + 32 * j;
         I.u0[j] = 0.0; I.u1[j] = 0.0; I.ya[j] = 0.0; I.yw[j] = 0.0;
@@ -419,6 +427,9 @@ L_step_begin:   // ---- PANOCEngine::step
             a = fma(t0, t0, fma(t1, t1, a));
         }
         if (dsqrt(warp_sum(a)) < CS->akkt_tol) { flag = false; goto L_step_return; }
+        // |gamma fpr| is below the tolerance but the AKKT residual |fpr| is not: the iteration goes on
+        // (counted: on this workload most of the iterations of a non-converging solve are of this kind)
+        MPCB_CS_LANE0(CS->n_small = CS->n_small + 1);
     }
     // update_lipschitz_constant: cost at the half step first
     MPCB_FORJ { pt0[j] = I.h0[j]; pt1[j] = I.h1[j]; }
@@ -626,7 +637,10 @@ L_finish:
         if (io.f1_infeas) io.f1_infeas[b] = CS->dy_plus / CS->c;
         if (io.f2_norm) io.f2_norm[b] = CS->f2n_plus;
         if (io.penalty) io.penalty[b] = CS->c;
-        if (io.evals) { io.evals[2 * b] = CS->n_cost; io.evals[2 * b + 1] = CS->n_grad; }
+        if (io.evals) {
+            io.evals[4 * b] = CS->n_cost; io.evals[4 * b + 1] = CS->n_grad;
+            io.evals[4 * b + 2] = CS->n_small; io.evals[4 * b + 3] = 0;
+        }
     }
     __syncwarp();   // lane 0's output block is done before the next instance resets the counters
     if (MODE != 0) goto L_fetch;

@@ -116,7 +116,7 @@ class BatchedSolver:
             n_inner=torch.empty(B, **i32), fpr=torch.empty(B, **f64),
             f1_infeas=torch.empty(B, **f64), f2_norm=torch.empty(B, **f64),
             penalty=torch.empty(B, **f64), y=torch.empty(B, d.n1, **f64),
-            evals=torch.empty(B, 2, **i32))
+            evals=torch.empty(B, 4, **i32))
 
     def run_batch(self, P, U0=None, Y0=None, C0=None, starts: int = 1, out=None):
         """Solve; returns a dict of CUDA tensors (asynchronous on the current stream)."""

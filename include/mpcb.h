@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MPCB_ABI_VERSION 1
+#define MPCB_ABI_VERSION 2
 
 /* ---- error codes --------------------------------------------------------- */
 #define MPCB_OK            0
@@ -126,9 +126,18 @@ void mpcb_default_solver_cfg(mpcb_solver_cfg* c);
 /*
  * Device workspace (bytes) the eval/solve entry points need for n_p parameter
  * rows: the staged structure-of-arrays copy of every row (K3 writes it, the
- * solve kernel reads it through L1 or TMA-loads it) plus a 4 KiB header holding
- * the work-queue counters (one per persistent CTA).
+ * solve kernel reads it through L1 or TMA-loads it) behind a header:
+ *   [0, MPCB_WS_COUNTER_BYTES)        work-queue counters (int32, one per persistent CTA)
+ *   then uint64[MPCB_WS_PROF_CTAS]    launch profile of the last mpcb_solve_f64: the
+ *                                     %globaltimer (ns) at which CTA c started, and
+ *   uint64[MPCB_WS_PROF_CTAS][MPCB_WS_PROF_WARPS]  at which warp w of CTA c ran out of work
+ *                                     (0: the warp did not take part) - read back by bench.py
+ *                                     to report the launch tail
  */
+#define MPCB_WS_COUNTER_BYTES 4096
+#define MPCB_WS_PROF_CTAS     1024
+#define MPCB_WS_PROF_WARPS    16
+#define MPCB_WS_HEADER_BYTES  (MPCB_WS_COUNTER_BYTES + MPCB_WS_PROF_CTAS * (1 + MPCB_WS_PROF_WARPS) * 8)
 int32_t mpcb_workspace_bytes(const mpcb_dims* dims, int32_t n_p, int32_t starts,
                              size_t* bytes);
 
@@ -162,8 +171,9 @@ int32_t mpcb_eval_f64(const mpcb_dims* dims, const mpcb_robot* robot,
  *   u_out[B,2N] solution, cost[B] (= f(u*)), exit_status[B] (MPCB_* above),
  *   n_outer[B], n_inner[B], fpr[B] last inner |gamma*fpr|, f1_infeas[B]
  *   (=|y+ - y|/c), f2_norm[B], penalty[B] final c, y_out[B,n1] multipliers,
- *   evals[B,2]: number of (cost-only, cost+gradient) horizon evaluations the
- *   kernel performed — feeds the work/roofline accounting.
+ *   evals[B,4]: {cost-only, cost+gradient} horizon evaluations the kernel performed
+ *   (feeds the work/roofline accounting), the number of inner iterations that started
+ *   with |gamma fpr| < tolerance but failed the AKKT test (so the solve went on), 0.
  */
 int32_t mpcb_solve_f64(const mpcb_dims* dims, const mpcb_robot* robot,
                        const mpcb_solver_cfg* cfg,

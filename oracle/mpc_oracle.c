@@ -598,7 +598,7 @@ typedef struct {
         u_plus[2 * MPCB_MAX_N];
     double gamma, sigma, L, cost, norm_gfpr, tau, lhs_ls, rhs_ls, akkt_tol;
     int iter;
-    long n_cost, n_grad;
+    long n_cost, n_grad, n_small;
 } panoc_t;
 
 static double psi_cost(panoc_t* S, const double* u)
@@ -722,6 +722,7 @@ static int panoc_step(panoc_t* S, double* u)
     if (S->iter >= 1) memcpy(S->grad_prev, S->grad, sizeof(double) * (size_t)n);
     compute_fpr(S, u);
     if (exit_condition(S)) return 0;
+    if (S->norm_gfpr < S->cfg->tolerance) S->n_small++;   /* AKKT test failed: the solve goes on */
     update_lipschitz(S, u);
     /* lbfgs_direction */
     lbfgs_update(&S->lb, S->gfpr, u);
@@ -791,9 +792,10 @@ static int panoc_solve(panoc_t* S, double* u, int* iters, int iters_left /* <= 0
 }
 
 /*
- * AlmOptimizer::solve for one instance.  out_scalars[10] =
+ * AlmOptimizer::solve for one instance.  out_scalars[11] =
  * {cost f(u*), last inner |gamma fpr|, f1_infeas, f2_norm, penalty c,
- *  n_outer, n_inner, n_cost_evals, n_grad_evals, exit_status}.
+ *  n_outer, n_inner, n_cost_evals, n_grad_evals, exit_status,
+ *  inner iterations with |gamma fpr| < tolerance that failed the AKKT test}.
  */
 int32_t mpco_solve(const mpcb_dims* d, const mpcb_robot* rb, const mpcb_solver_cfg* cfg,
                    const double* p, const double* u0, const double* y0, const double* c0,
@@ -900,6 +902,7 @@ int32_t mpco_solve(const mpcb_dims* d, const mpcb_robot* rb, const mpcb_solver_c
         out_scalars[7] = (double)S->n_cost;
         out_scalars[8] = (double)S->n_grad;
         out_scalars[9] = (double)exit_status;
+        out_scalars[10] = (double)S->n_small;
     }
     free(F2);
     free(S);
@@ -910,7 +913,7 @@ int32_t mpco_solve(const mpcb_dims* d, const mpcb_robot* rb, const mpcb_solver_c
 int32_t mpco_solve_batch(const mpcb_dims* d, const mpcb_robot* rb,
                          const mpcb_solver_cfg* cfg, int32_t n_p, int32_t starts,
                          const double* p, const double* u0, double* u_out,
-                         double* out_scalars /* [B,10] */, int32_t threads)
+                         double* out_scalars /* [B,11] */, int32_t threads)
 {
     const int np = make_layout(d).np, n = 2 * d->N;
     const long B = (long)n_p * starts;
@@ -920,7 +923,7 @@ int32_t mpco_solve_batch(const mpcb_dims* d, const mpcb_robot* rb,
 #endif
     for (long b = 0; b < B; ++b) {
         int r = mpco_solve(d, rb, cfg, p + (b / starts) * np, u0 ? u0 + b * n : 0, 0, 0,
-                           u_out + b * n, 0, out_scalars ? out_scalars + b * 10 : 0);
+                           u_out + b * n, 0, out_scalars ? out_scalars + b * 11 : 0);
         if (r) rc = r;
     }
     return rc;

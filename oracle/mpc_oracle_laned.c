@@ -699,7 +699,7 @@ typedef struct {
 typedef struct {
     lanes_t u0, u1, g0, g1, gp0, gp1, h0, h1, r0, r1, d0, d1, s0, s1, ya, yw;
     double c, gamma, sigma, Lc, cost, norm_r, akkt_tol;
-    int iter, n_cost, n_grad;
+    int iter, n_cost, n_grad, n_small;
 } inst_t;
 
 #define FORJL for (int j = 0; j < J; ++j) for (int l = 0; l < W; ++l)
@@ -847,6 +847,7 @@ static int panoc_step(const mpcb_solver_cfg* cfg, const scen_t* S, inst_t* I, lb
             p[l] = a;
         }
         if (sqrt(warp_sum(p)) < I->akkt_tol) return 0;
+        I->n_small++;   /* |gamma fpr| < tolerance, AKKT test failed: the solve goes on */
     }
     eval_at(S, I, I->h0, I->h1, I->c, 0, &o);
     double cost_half = o.psi;
@@ -926,8 +927,9 @@ static int panoc_step(const mpcb_solver_cfg* cfg, const scen_t* S, inst_t* I, lb
 }
 
 /* out_scalars as mpco_solve: {cost, fpr, f1_infeas, f2_norm, penalty, n_outer, n_inner,
- * n_cost, n_grad, exit_status}; n_cost / n_grad count the kernel's evaluations (cost-only,
- * cost+gradient). */
+ * n_cost, n_grad, exit_status, n_small}; n_cost / n_grad count the kernel's evaluations (cost-only,
+ * cost+gradient), n_small the inner iterations that met |gamma fpr| < tolerance but not the AKKT
+ * test. */
 int32_t mpcl_solve(const mpcb_dims* d, const mpcb_robot* rb, const mpcb_solver_cfg* cfg,
                    const double* p, const double* u0, const double* y0, const double* c0,
                    double* u_out, double* y_out, double* out_scalars)
@@ -1064,6 +1066,7 @@ int32_t mpcl_solve(const mpcb_dims* d, const mpcb_robot* rb, const mpcb_solver_c
         out_scalars[7] = I->n_cost;
         out_scalars[8] = I->n_grad;
         out_scalars[9] = status;
+        out_scalars[10] = I->n_small;
     }
     free(I); free(B);
     scen_free(&Sc);
@@ -1082,7 +1085,7 @@ int32_t mpcl_solve_batch(const mpcb_dims* d, const mpcb_robot* rb, const mpcb_so
 #endif
     for (long b = 0; b < B; ++b) {
         int r = mpcl_solve(d, rb, cfg, p + (b / starts) * np, u0 ? u0 + b * n : 0, 0, 0, u_out + b * n,
-                           0, out_scalars ? out_scalars + b * 10 : 0);
+                           0, out_scalars ? out_scalars + b * 11 : 0);
         if (r) rc = r;
     }
     return rc;

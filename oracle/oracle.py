@@ -76,7 +76,7 @@ def evaluate(dims, robot, p, u, y=None, c=10.0, want_grad=True, laned=False):
 
 
 SCALARS = ("cost", "fpr", "f1_infeas", "f2_norm", "penalty", "n_outer", "n_inner",
-           "n_cost", "n_grad", "exit_status")
+           "n_cost", "n_grad", "exit_status", "n_small")
 
 
 def solve(dims, robot, cfg, p, u0=None, y0=None, c0=None, laned=False):
@@ -86,14 +86,14 @@ def solve(dims, robot, cfg, p, u0=None, y0=None, c0=None, laned=False):
     p, u0, y0 = _c(p), _c(u0), _c(y0)
     u = np.zeros(dims.nu_total)
     y = np.zeros(dims.n1)
-    sc = np.zeros(10)
+    sc = np.zeros(11)
     c0p = None if c0 is None else ctypes.byref(ctypes.c_double(c0))
     rc = fn(ctypes.byref(cd), ctypes.byref(cr), ctypes.byref(cc), _p(p), _p(u0),
                       _p(y0), c0p, _p(u), _p(y), _p(sc))
     if rc:
         raise RuntimeError(f"mpco_solve failed: {rc}")
     out = dict(zip(SCALARS, sc.tolist()))
-    for k in ("n_outer", "n_inner", "n_cost", "n_grad", "exit_status"):
+    for k in ("n_outer", "n_inner", "n_cost", "n_grad", "exit_status", "n_small"):
         out[k] = int(out[k])
     out["u"] = u
     out["y"] = y
@@ -108,7 +108,7 @@ def solve_batch(dims, robot, cfg, P, U0=None, starts=1, threads=1, laned=False):
     n_p = P.shape[0]
     B = n_p * starts
     U = np.zeros((B, dims.nu_total))
-    SC = np.zeros((B, 10))
+    SC = np.zeros((B, 11))
     if laned:
         rc = L.mpcl_solve_batch(ctypes.byref(cd), ctypes.byref(cr), ctypes.byref(cc),
                                 ctypes.c_int32(n_p), ctypes.c_int32(starts), _p(P), _p(U0),

@@ -19,7 +19,7 @@ for it in range(passes):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); o = s.run_batch(Pd, Ud, starts=wl.starts); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    ev = o["evals"].double().sum(0)
+    ev = o["evals"][:, :2].double().sum(0)
     print(f"{wl.name} n={n}x{wl.starts} {kw}: {ms:.1f} ms  {n*wl.starts/ms*1e3:.1f} solves/s  "
           f"{float(ev.sum())/ms*1e3/1e6:.3f} Mevals/s  conv {float((o['exit_status']==0).double().mean()):.3f} "
-          f"inner {o['n_inner'].double().mean().item():.0f} evals {o['evals'].double().mean(0).tolist()}")
+          f"inner {o['n_inner'].double().mean().item():.0f} evals {o['evals'][:, :2].double().mean(0).tolist()}")

@@ -27,7 +27,7 @@ def test_laned_oracle_reproduces_committed_solves(fixture, name):
     U, SC = oracle.solve_batch(dims, RobotSpec(), SolverSettings(**sk), fixture[name + "/P"],
                                fixture[name + "/U0"], starts=starts, threads=os.cpu_count() or 1, laned=True)
     np.testing.assert_array_equal(U, fixture[name + "/U"])
-    np.testing.assert_array_equal(SC, fixture[name + "/SC"])
+    np.testing.assert_array_equal(SC[:, :10], fixture[name + "/SC"])   # (column 10, n_small, was added later)
 
 
 @pytest.mark.gpu
