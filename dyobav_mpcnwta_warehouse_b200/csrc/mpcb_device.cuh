@@ -79,6 +79,7 @@ struct KParams {
     int cull;            // 1: skip provably-zero obstacle terms
     int budget;          // > 0: cap on the inner iterations of one solve (cfg->max_inner_total)
     unsigned long long* prof;   // launch profile in the workspace header (nullable): [CTAS] start, [CTAS][WARPS] finish
+    const int* order;           // queue slot -> scenario, hardest first (nullable: identity)
 };
 #include "../../include/mpcb.h"     // MPCB_WS_PROF_CTAS / MPCB_WS_PROF_WARPS
 

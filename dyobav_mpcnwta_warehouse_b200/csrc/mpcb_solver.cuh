@@ -280,6 +280,7 @@ L_fetch:
             t = __shfl_sync(FULL, t, 0);
             if (t < nsc_q * P.starts) {
                 sc = q + (t / P.starts) * nq;
+                if (P.order) sc = P.order[sc];
                 b = sc * P.starts + t % P.starts;
                 CS->qscan = qs;
                 break;

@@ -133,6 +133,9 @@ void mpcb_default_solver_cfg(mpcb_solver_cfg* c);
  *   uint64[MPCB_WS_PROF_CTAS][MPCB_WS_PROF_WARPS]  at which warp w of CTA c ran out of work
  *                                     (0: the warp did not take part) - read back by bench.py
  *                                     to report the launch tail
+ * followed by the scenario order of the solve (int32[n_p], float[n_p] difficulty keys: the solve
+ * kernel starts with the scenarios whose reference path an obstacle blocks, which are the ones
+ * that use up the iteration caps) and then the staged blocks.
  */
 #define MPCB_WS_COUNTER_BYTES 4096
 #define MPCB_WS_PROF_CTAS     1024
