@@ -28,7 +28,7 @@ class CSim(ctypes.Structure):
                 + [(n, ctypes.c_double) for n in ("base_speed", "lin_vel_max", "ped_size", "stc_w", "dyn_w", "ts")]
                 + [("tuning", ctypes.c_double * 10)]
                 + [(n, ctypes.c_void_p) for n in ("state", "last_u", "ref_traj", "ref_len", "idx_ref", "goal",
-                                                   "polys", "n_poly", "ped_pos", "ped_vel", "done")])
+                                                   "polys", "n_poly", "ped_pos", "ped_vel", "done", "od_in")])
 
 
 def load():

@@ -89,7 +89,8 @@ class ClosedLoopBatch:
     # -- one parameter row, the way the reference's host code builds it
     def _row(self, e: Episode) -> List[float]:
         d, N = self.dims, self.dims.N
-        ref_states, e.idx_ref = packing.ref_states_window(e.idx_ref, e.ref_traj, e.state, 1, N)
+        # the reference passes N_hor into `action_steps` (trajectory_tracker.py:187): window [idx-N, idx+5N)
+        ref_states, e.idx_ref = packing.ref_states_window(e.idx_ref, e.ref_traj, e.state, N, N)
         goal = e.ref_path[-1]
         gx, gy = e.state[0] - goal[0], e.state[1] - goal[1]
         dist_to_goal = math.sqrt(gx * gx + gy * gy)
@@ -108,13 +109,11 @@ class ClosedLoopBatch:
                     slots.append([c[0], c[1], r, r, 0, 1])
                 obs.append(slots)
         obs = obs[: d.Ndyn]
-        # static obstacles: the Nstcobs closest polygons (mpc_interface.py:90-100)
+        # static obstacles: the Nstcobs polygons closest by EDGE distance (mpc_interface.py:90-100,
+        # utils_geo.py:6-33), nearest first
         stc = [0.0] * (d.Nstc * 3 * d.nedge)
         if e.polygons:
-            dist = [min(math.sqrt((vx - e.state[0]) * (vx - e.state[0]) + (vy - e.state[1]) * (vy - e.state[1]))
-                        for vx, vy in np.asarray(p)) for p in e.polygons]
-            order = np.argsort(dist, kind="stable")[: d.Nstc]
-            for slot, i in enumerate(order):
+            for slot, i in enumerate(packing.closest_polygons(e.state, e.polygons, d.Nstc)):
                 b, a0, a1 = e._halfspaces[i]
                 stc[slot * 3 * d.nedge:(slot + 1) * 3 * d.nedge] = b + a0 + a1
         return packing.assemble_params(d, self.cfg, e.state, ref_states, speed_ref, last_u=e.last_u,
@@ -130,8 +129,10 @@ class ClosedLoopBatch:
         u, cost, status = self.solve(P)
         for e, ue, ce, se in zip(live, np.asarray(u), np.asarray(cost), np.asarray(status)):
             a = np.array(ue[:2], dtype=np.float64)         # action_steps = 1
+            e.last_u = a                                    # past_actions keeps the solver's action (:329)
+            if a[0] < 0:                                    # no-backward rule of the sim loop (main_base.py:320-321)
+                a = np.zeros(2)
             e.state = unicycle_rk4(e.state, a, self.ts, self.sincos)
-            e.last_u = a
             e.states.append(e.state.copy()); e.actions.append(a); e.costs.append(float(ce)); e.statuses.append(int(se))
             for p in e.pedestrians:
                 p.position = p.position + self.ts * p.mode_velocities[0]

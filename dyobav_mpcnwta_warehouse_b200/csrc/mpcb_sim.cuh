@@ -2,12 +2,13 @@
 //
 // K4 pack_kernel: one CTA per episode builds its parameter row p, in the reference layout
 //   (mpc_builder.py:47-60), the way the reference's host code does every timestep:
-//   reference window    TrajectoryTracker.get_ref_states        (trajectory_tracker.py:243-270)
+//   reference window    TrajectoryTracker.get_ref_states        (trajectory_tracker.py:243-270),
+//                       searched in [idx - N_hor, idx + 5 N_hor) as the reference's call does (:187)
 //   speed reference     run_step incl. its max() quirk          (:304-310)
 //   o_d                 MainBase.run_one_step ellipse list      (main_base.py:293-302) from
 //                       constant-velocity pedestrian modes, MpcInterface.get_dyn_constraints
-//   o_s                 the Nstcobs closest polygons -> half-spaces (mpc_interface.py:73-100,
-//                       utils_geo.py:35-62 normalisation)
+//   o_s                 the Nstcobs polygons closest by edge distance -> half-spaces
+//                       (mpc_interface.py:73-100, utils_geo.py:6-62)
 //   concatenation       trajectory_tracker.py:315-317
 // K5 plant_kernel: RK4 unicycle step with the first action (motion_model.py:141-163),
 //   pedestrians advance, termination test (trajectory_tracker.py:191-199).
@@ -37,6 +38,8 @@ struct SimArgs {
     double* ped_pos;       // [n,Pd,2]
     const double* ped_vel; // [n,Pd,M,2]
     int* done;             // [n]
+    const double* od_in;   // [n,Ndyn,N+1,6] or NULL: the o_d block as a predictor stage produced it
+                           // (K6, or any host predictor); NULL: built from the pedestrian modes
 };
 
 __global__ void __launch_bounds__(64) pack_kernel(const Lay L, const SimArgs A, double* __restrict__ Pout)
@@ -50,11 +53,12 @@ __global__ void __launch_bounds__(64) pack_kernel(const Lay L, const SimArgs A, 
     __shared__ int s_idx;
     __shared__ int s_slot[64];
     if (tid == 0) {
-        // closest reference sample within [idx-1, idx+5)
+        // closest reference sample within [idx - N, idx + 5N): the reference calls get_ref_states
+        // with N_hor in the `action_steps` slot (trajectory_tracker.py:187,253-254)
         const int len = A.ref_len[e];
         const int idx0 = A.idx_ref[e];
-        const int lb = idx0 - 1 > 0 ? idx0 - 1 : 0;
-        const int ub = len < idx0 + 5 ? len : idx0 + 5;
+        const int lb = idx0 - N > 0 ? idx0 - N : 0;
+        const int ub = len < idx0 + 5 * N ? len : idx0 + 5 * N;
         double best = INFINITY;
         int bi = lb;
         for (int i = lb; i < ub; ++i) {
@@ -66,7 +70,9 @@ __global__ void __launch_bounds__(64) pack_kernel(const Lay L, const SimArgs A, 
         s_idx = bi;
         A.idx_ref[e] = bi;
     }
-    // rank the polygons by their closest vertex (stable: ties by index)
+    // rank the polygons by their distance to the robot, measured to the EDGES as
+    // utils_geo.lineseg_dists does for MpcInterface.get_closest_n_stc_obstacles (utils_geo.py:6-33,
+    // mpc_interface.py:90-100); stable: ties by index
     const int np_ = A.n_poly[e];
     for (int i = tid; i < 64; i += nt) s_slot[i] = -1;
     __syncthreads();
@@ -75,8 +81,17 @@ __global__ void __launch_bounds__(64) pack_kernel(const Lay L, const SimArgs A, 
         const double* v = A.polys + ((size_t)e * A.Kp + i) * 8;
         double m = INFINITY;
         for (int k = 0; k < 4; ++k) {
-            const double dx = v[2 * k] - sx, dy = v[2 * k + 1] - sy;
-            const double d = sqrt(dx * dx + dy * dy);
+            const int k1 = (k + 1) & 3;
+            const double ax = v[2 * k], ay = v[2 * k + 1], bx = v[2 * k1], by = v[2 * k1 + 1];
+            const double ex = bx - ax, ey = by - ay;
+            const double ln = sqrt(ex * ex + ey * ey);
+            const double dx = ex / ln, dy = ey / ln;
+            const double s_ = (ax - sx) * dx + (ay - sy) * dy;
+            const double t_ = (sx - bx) * dx + (sy - by) * dy;
+            double h = s_ > t_ ? s_ : t_;
+            h = h > 0.0 ? h : 0.0;
+            const double c = (sx - ax) * dy - (sy - ay) * dx;
+            const double d = sqrt(h * h + c * c);
             m = d < m ? d : m;
         }
         s_pd[i] = m;
@@ -148,6 +163,11 @@ __global__ void __launch_bounds__(64) pack_kernel(const Lay L, const SimArgs A, 
     for (int i = tid; i < L.Ndyn * (N + 1); i += nt) {
         const int ob = i / (N + 1), t = i - ob * (N + 1);
         double* o = p + L.p_od + (size_t)i * 6;
+        if (A.od_in) {                       // supplied by the predictor stage
+            const double* src = A.od_in + ((size_t)e * L.Ndyn * (N + 1) + i) * 6;
+            for (int k = 0; k < 6; ++k) o[k] = src[k];
+            continue;
+        }
         if (ob >= nobs) { for (int k = 0; k < 6; ++k) o[k] = 0.0; continue; }
         const int pd = ob / A.M, md = ob - pd * A.M;
         const double* pos = A.ped_pos + ((size_t)e * A.Pd + pd) * 2;
@@ -168,7 +188,10 @@ __global__ void plant_kernel(const SimArgs A, int N2, const double* __restrict__
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= A.n || A.done[e]) return;
-    const double v = u[(size_t)e * N2], w = u[(size_t)e * N2 + 1];
+    const double v_sol = u[(size_t)e * N2], w_sol = u[(size_t)e * N2 + 1];
+    // the sim loop never drives backwards: a negative speed is replaced by a full stop
+    // (main_base.py:320-321); the tracker still remembers the solver's own action (:329)
+    const double v = v_sol < 0.0 ? 0.0 : v_sol, w = v_sol < 0.0 ? 0.0 : w_sol;
     double s[3] = {A.state[3 * e], A.state[3 * e + 1], A.state[3 * e + 2]};
     const double ts = A.ts;
     double k1[3], k2[3], k3[3], k4[3], sn, cs;
@@ -183,7 +206,7 @@ __global__ void plant_kernel(const SimArgs A, int N2, const double* __restrict__
 #pragma unroll
     for (int i = 0; i < 3; ++i) s[i] = s[i] + (1.0 / 6.0) * (k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i]);
     A.state[3 * e] = s[0]; A.state[3 * e + 1] = s[1]; A.state[3 * e + 2] = s[2];
-    A.last_u[2 * e] = v; A.last_u[2 * e + 1] = w;
+    A.last_u[2 * e] = v_sol; A.last_u[2 * e + 1] = w_sol;
     for (int pd = 0; pd < A.Pd; ++pd) {
         double* pos = A.ped_pos + ((size_t)e * A.Pd + pd) * 2;
         const double* vel = A.ped_vel + ((size_t)e * A.Pd + pd) * A.M * 2;   // mode 0 is what happens

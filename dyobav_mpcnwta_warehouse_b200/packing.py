@@ -129,7 +129,14 @@ def ref_traj_from_path(ts: float, ref_path: Sequence[Tuple[float, float]], state
 
 def ref_states_window(idx_ref_traj: int, ref_traj, state, action_steps: int = 1,
                       horizon: int = 20):
-    """Next ``horizon`` reference states from the closest trajectory sample, padded with the last."""
+    """Next ``horizon`` reference states from the closest trajectory sample, padded with the last
+    (``TrajectoryTracker.get_ref_states``, trajectory_tracker.py:243-270).
+
+    The closest sample is searched in ``[idx - action_steps, idx + 5*action_steps)``.  NOTE the
+    reference's own call (``set_ref_states``, :187) passes ``N_hor`` POSITIONALLY into
+    ``action_steps`` and leaves ``horizon`` at its default 20: the effective window is
+    ``[idx - N_hor, idx + 5*N_hor)``.  Callers that mirror the reference (closed_loop.py, the device
+    packer K4) therefore pass ``action_steps=N_hor``."""
     lb = max(0, idx_ref_traj - action_steps)
     ub = min(len(ref_traj), idx_ref_traj + 5 * action_steps)
     # sqrt(dx*dx + dy*dy) instead of the reference's math.hypot (trajectory_tracker.py:257): the
@@ -141,6 +148,39 @@ def ref_states_window(idx_ref_traj: int, ref_traj, state, action_steps: int = 1,
     while len(win) < horizon:
         win.append(ref_traj[-1])
     return np.asarray(win, dtype=np.float64), idx
+
+
+def point_to_polygon_distance(px: float, py: float, poly) -> float:
+    """Smallest distance from a point to the EDGES of a polygon, as ``utils_geo.lineseg_dists``
+    computes it for ``MpcInterface.get_closest_n_stc_obstacles`` (utils_geo.py:6-33,
+    mpc_interface.py:90-100): along-edge overshoot ``h = max(s, t, 0)`` and perpendicular offset
+    ``c`` of the unit tangent, ``d = |(h, c)|``.  (sqrt of the sum of squares where the reference
+    uses np.hypot: the device packer reproduces it bit for bit.)"""
+    V = np.asarray(poly, dtype=np.float64)
+    m = V.shape[0]
+    best = math.inf
+    for i in range(m):
+        ax, ay = float(V[i, 0]), float(V[i, 1])
+        bx, by = float(V[(i + 1) % m, 0]), float(V[(i + 1) % m, 1])
+        ex, ey = bx - ax, by - ay
+        ln = math.sqrt(ex * ex + ey * ey)
+        dx, dy = ex / ln, ey / ln
+        s_ = (ax - px) * dx + (ay - py) * dy
+        t_ = (px - bx) * dx + (py - by) * dy
+        h = max(s_, t_, 0.0)
+        c = (px - ax) * dy - (py - ay) * dx
+        d = math.sqrt(h * h + c * c)
+        best = d if d < best else best
+    return best
+
+
+def closest_polygons(state, polygons, n_keep: int) -> List[int]:
+    """Indices of the ``n_keep`` polygons closest (by edge distance) to the robot, nearest first.
+    The reference keeps the same SET (np.argpartition, mpc_interface.py:97) in numpy's unspecified
+    partition order; the order only permutes the polygon slots of ``o_s`` (a sum over polygons)."""
+    d = [point_to_polygon_distance(float(state[0]), float(state[1]), p) for p in polygons]
+    order = sorted(range(len(polygons)), key=lambda i: (d[i], i))
+    return order[:n_keep]
 
 
 def assemble_params(dims: Dims, cfg: MpcConfig, state, ref_states: np.ndarray,

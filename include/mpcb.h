@@ -230,6 +230,9 @@ typedef struct mpcb_sim {
     double* ped_pos;        /* [n,Pd,2] in/out                                       */
     const double* ped_vel;  /* [n,Pd,M,2]; mode 0 is the motion that happens         */
     int32_t* done;          /* [n] in/out                                            */
+    const double* od_in;    /* [n,Ndyn,N+1,6] or NULL: the o_d block from a predictor
+                             * stage (mpcb_cluster_f64 or the host); NULL: built from
+                             * the pedestrians' constant-velocity modes               */
 } mpcb_sim;
 
 int32_t mpcb_pack_f64(const mpcb_dims* dims, const mpcb_sim* sim, double* p_out, void* stream);
