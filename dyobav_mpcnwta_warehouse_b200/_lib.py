@@ -18,7 +18,8 @@ ERRORS = {-1: "unsupported or inconsistent dimensions", -2: "required pointer is
 # every symbol include/mpcb.h declares
 EXPORTS = ("mpcb_abi_version", "mpcb_last_error", "mpcb_param_len", "mpcb_num_decision", "mpcb_n1",
            "mpcb_n2", "mpcb_team_groups", "mpcb_default_robot", "mpcb_default_solver_cfg", "mpcb_workspace_bytes",
-           "mpcb_eval_f64", "mpcb_solve_f64", "mpcb_solve_one_host", "mpcb_pack_f64",
+           "mpcb_eval_f64", "mpcb_solve_f64", "mpcb_workspace_bytes_f32", "mpcb_eval_f32", "mpcb_solve_f32",
+           "mpcb_solve_one_host", "mpcb_pack_f64",
            "mpcb_plant_step_f64", "mpcb_sincos_host", "mpcb_cluster_f64", "mpcb_fp64_peak_tflops")
 
 
@@ -56,6 +57,12 @@ def load():
     L.mpcb_eval_f64.argtypes = [pd, pr, pc, i32, i32] + [dp] * 9 + [vp, ctypes.c_size_t, vp]
     L.mpcb_solve_f64.restype = i32
     L.mpcb_solve_f64.argtypes = [pd, pr, pc, i32, i32] + [dp] * 15 + [vp, ctypes.c_size_t, vp]
+    L.mpcb_workspace_bytes_f32.restype = i32
+    L.mpcb_workspace_bytes_f32.argtypes = [pd, i32, i32, ctypes.POINTER(ctypes.c_size_t)]
+    L.mpcb_eval_f32.restype = i32
+    L.mpcb_eval_f32.argtypes = [pd, pr, pc, i32, i32] + [dp] * 9 + [vp, ctypes.c_size_t, vp]
+    L.mpcb_solve_f32.restype = i32
+    L.mpcb_solve_f32.argtypes = [pd, pr, pc, i32, i32] + [dp] * 15 + [vp, ctypes.c_size_t, vp]
     L.mpcb_solve_one_host.restype = i32
     L.mpcb_solve_one_host.argtypes = [pd, pr, pc] + [dp] * 8
     L.mpcb_pack_f64.restype = i32

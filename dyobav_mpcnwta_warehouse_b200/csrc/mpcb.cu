@@ -1077,6 +1077,146 @@ int32_t mpcb_cluster_f64(const mpcb_dims* d, int32_t n, int32_t K, int32_t H, do
     return MPCB_OK;
 }
 
+/* ---- f32 twins: single-precision buffers at the boundary ------------------------
+ * The arithmetic stays f64.  PANOC's Lipschitz probe perturbs the iterate by 1e-12 (below f32
+ * resolution) and the 1e-6 radius regulariser makes the ellipse terms reach 1e12 x distance^2
+ * (SURVEY Appendix B-2, C-11): neither survives single precision, so the f32 mode is a boundary
+ * mode - parameters, guesses and results travel as float32 (half the host<->device bytes), are
+ * widened exactly on the device, solved by the f64 kernels, and the results rounded once.  The
+ * outputs therefore equal the f64 entry point's on the widened inputs, rounded to f32. */
+namespace {
+__global__ void widen_kernel(const float* __restrict__ a, double* __restrict__ b, size_t n)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        b[i] = (double)a[i];
+}
+__global__ void narrow_kernel(const double* __restrict__ a, float* __restrict__ b, size_t n)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        b[i] = (float)a[i];
+}
+inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
+struct F32Layout {
+    size_t ws64, p, u0, y0, c0, u, y, sc, total;   // byte offsets inside the workspace; sc: 5 x [B] scalars
+};
+int f32_layout(const mpcb_dims* d, int32_t n_p, int32_t starts, F32Layout& F)
+{
+    Lay L;
+    int rc = build_layout(d, L);
+    if (rc) return rc;
+    if (n_p < 1 || starts < 1) return MPCB_E_DIMS;
+    size_t ws = 0;
+    rc = mpcb_workspace_bytes(d, n_p, starts, &ws);
+    if (rc) return rc;
+    const size_t B = (size_t)n_p * starts, n = 2 * (size_t)d->N;
+    F.ws64 = up256(ws);
+    F.p = F.ws64;
+    F.u0 = F.p + up256((size_t)n_p * L.np * 8);
+    F.y0 = F.u0 + up256(B * n * 8);
+    F.c0 = F.y0 + up256(B * n * 8);
+    F.u = F.c0 + up256(B * 8);
+    F.y = F.u + up256(B * n * 8);
+    F.sc = F.y + up256(B * n * 8);
+    F.total = F.sc + 5 * up256(B * 8);
+    return MPCB_OK;
+}
+void widen(const float* a, void* base, size_t off, size_t n, cudaStream_t st)
+{
+    if (a && n) widen_kernel<<<(unsigned)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096), 256, 0, st>>>(
+        a, reinterpret_cast<double*>(reinterpret_cast<char*>(base) + off), n);
+}
+void narrow(void* base, size_t off, float* b, size_t n, cudaStream_t st)
+{
+    if (b && n) narrow_kernel<<<(unsigned)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096), 256, 0, st>>>(
+        reinterpret_cast<const double*>(reinterpret_cast<char*>(base) + off), b, n);
+}
+}  // namespace
+
+int32_t mpcb_workspace_bytes_f32(const mpcb_dims* d, int32_t n_p, int32_t starts, size_t* bytes)
+{
+    if (!bytes) return MPCB_E_NULL;
+    F32Layout F;
+    int rc = f32_layout(d, n_p, starts, F);
+    if (rc) return rc;
+    *bytes = F.total;
+    return MPCB_OK;
+}
+
+int32_t mpcb_solve_f32(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solver_cfg* c, int32_t n_p,
+                       int32_t starts, const float* p, const float* u0, const float* y0, const float* c0,
+                       float* u_out, float* cost, int32_t* exit_status, int32_t* n_outer, int32_t* n_inner,
+                       float* fpr, float* f1_infeas, float* f2_norm, float* penalty, float* y_out,
+                       int32_t* evals, void* workspace, size_t ws_bytes, void* stream)
+{
+    if (!p || !u_out || !exit_status || !workspace) return MPCB_E_NULL;
+    F32Layout F;
+    int rc = f32_layout(d, n_p, starts, F);
+    if (rc) return rc;
+    if (ws_bytes < F.total) return MPCB_E_WORKSPACE;
+    if (reinterpret_cast<uintptr_t>(workspace) & 255) return MPCB_E_ALIGN;
+    Lay L;
+    build_layout(d, L);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t B = (size_t)n_p * starts, n = 2 * (size_t)d->N;
+    char* w = reinterpret_cast<char*>(workspace);
+    auto dp = [&](size_t off) { return reinterpret_cast<double*>(w + off); };
+    widen(p, w, F.p, (size_t)n_p * L.np, st);
+    widen(u0, w, F.u0, B * n, st);
+    widen(y0, w, F.y0, B * n, st);
+    widen(c0, w, F.c0, B, st);
+    const size_t s1 = up256(B * 8);
+    rc = mpcb_solve_f64(d, r, c, n_p, starts, dp(F.p), u0 ? dp(F.u0) : nullptr, y0 ? dp(F.y0) : nullptr,
+                        c0 ? dp(F.c0) : nullptr, dp(F.u), dp(F.sc), exit_status, n_outer, n_inner, dp(F.sc + s1),
+                        dp(F.sc + 2 * s1), dp(F.sc + 3 * s1), dp(F.sc + 4 * s1), dp(F.y), evals, workspace, F.ws64, stream);
+    if (rc) return rc;
+    narrow(w, F.u, u_out, B * n, st);
+    narrow(w, F.y, y_out, B * n, st);
+    narrow(w, F.sc, cost, B, st);
+    narrow(w, F.sc + s1, fpr, B, st);
+    narrow(w, F.sc + 2 * s1, f1_infeas, B, st);
+    narrow(w, F.sc + 3 * s1, f2_norm, B, st);
+    narrow(w, F.sc + 4 * s1, penalty, B, st);
+    CUDA_TRY(cudaGetLastError());
+    return MPCB_OK;
+}
+
+int32_t mpcb_eval_f32(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solver_cfg* c, int32_t n_p,
+                      int32_t starts, const float* p, const float* u, const float* y, const float* cpen,
+                      float* f, float* psi, float* grad, float* F1, float* F2, void* workspace, size_t ws_bytes,
+                      void* stream)
+{
+    if (!p || !u || !workspace) return MPCB_E_NULL;
+    F32Layout F;
+    int rc = f32_layout(d, n_p, starts, F);
+    if (rc) return rc;
+    const size_t B = (size_t)n_p * starts, n = 2 * (size_t)d->N, n2 = d->Ndyn > 0 ? d->Ndyn : 1;
+    // F2 [B, n2] does not fit the solve layout's scalar slots in general: it follows the layout
+    const size_t oF2 = F.total, need = F.total + up256(B * n2 * 8);
+    if (ws_bytes < need) return MPCB_E_WORKSPACE;
+    if (reinterpret_cast<uintptr_t>(workspace) & 255) return MPCB_E_ALIGN;
+    Lay L;
+    build_layout(d, L);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    char* w = reinterpret_cast<char*>(workspace);
+    auto dp = [&](size_t off) { return reinterpret_cast<double*>(w + off); };
+    widen(p, w, F.p, (size_t)n_p * L.np, st);
+    widen(u, w, F.u0, B * n, st);
+    widen(y, w, F.y0, B * n, st);
+    widen(cpen, w, F.c0, B, st);
+    const size_t s1 = up256(B * 8);
+    // slots: f -> sc[0], psi -> sc[1], grad -> u, F1 -> y, F2 -> after the layout
+    rc = mpcb_eval_f64(d, r, c, n_p, starts, dp(F.p), dp(F.u0), y ? dp(F.y0) : nullptr, cpen ? dp(F.c0) : nullptr,
+                       dp(F.sc), dp(F.sc + s1), dp(F.u), dp(F.y), dp(oF2), workspace, F.ws64, stream);
+    if (rc) return rc;
+    narrow(w, F.sc, f, B, st);
+    narrow(w, F.sc + s1, psi, B, st);
+    narrow(w, F.u, grad, B * n, st);
+    narrow(w, F.y, F1, B * n, st);
+    narrow(w, oF2, F2, B * n2, st);
+    CUDA_TRY(cudaGetLastError());
+    return MPCB_OK;
+}
+
 /* Measured FP64 FMA throughput of the current device in TFLOP/s (2 flop per FMA). */
 int32_t mpcb_fp64_peak_tflops(double* tflops)
 {

@@ -142,6 +142,72 @@ class BatchedSolver:
         return o
 
 
+    # -- f32 boundary mode (include/mpcb.h "f32 twins"): float32 tensors in and out, f64 arithmetic
+    def _workspace_f32(self, n_p: int, starts: int, extra: int = 0):
+        torch = self._torch
+        need = ctypes.c_size_t()
+        _lib.check(self.lib.mpcb_workspace_bytes_f32(ctypes.byref(self._cd), n_p, starts, ctypes.byref(need)),
+                   "mpcb_workspace_bytes_f32")
+        total = need.value + extra + 256
+        if getattr(self, "_ws32", None) is None or self._ws32.numel() < total or self._ws32.device != self.device:
+            self._ws32 = torch.empty(total, dtype=torch.uint8, device=self.device)
+        off = (-self._ws32.data_ptr()) % 256              # the entry points want 256-byte alignment
+        return self._ws32[off:off + need.value + extra]
+
+    def run_batch_f32(self, P, U0=None, Y0=None, C0=None, starts: int = 1):
+        """``run_batch`` with float32 CUDA tensors at the boundary (``mpcb_solve_f32``): the results
+        equal the f64 solve of the widened inputs, rounded to float32."""
+        torch = self._torch
+        d = self.dims
+        n_p = P.shape[0]
+        B = n_p * starts
+        f32 = torch.float32
+        self._chk(P, (n_p, d.np), "P", f32)
+        self._chk(U0, (B, d.nu_total), "U0", f32)
+        self._chk(Y0, (B, d.n1), "Y0", f32)
+        self._chk(C0, (B,), "C0", f32)
+        with torch.cuda.device(self.device):
+            ws = self._workspace_f32(n_p, starts)
+            kf = dict(device=self.device, dtype=f32)
+            ki = dict(device=self.device, dtype=torch.int32)
+            o = dict(u=torch.empty(B, d.nu_total, **kf), cost=torch.empty(B, **kf),
+                     exit_status=torch.empty(B, **ki), n_outer=torch.empty(B, **ki), n_inner=torch.empty(B, **ki),
+                     fpr=torch.empty(B, **kf), f1_infeas=torch.empty(B, **kf), f2_norm=torch.empty(B, **kf),
+                     penalty=torch.empty(B, **kf), y=torch.empty(B, d.n1, **kf), evals=torch.empty(B, 4, **ki))
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            rc = self.lib.mpcb_solve_f32(
+                ctypes.byref(self._cd), ctypes.byref(self._cr), ctypes.byref(self._cc), n_p, starts,
+                _ptr(P), _ptr(U0), _ptr(Y0), _ptr(C0), _ptr(o["u"]), _ptr(o["cost"]), _ptr(o["exit_status"]),
+                _ptr(o["n_outer"]), _ptr(o["n_inner"]), _ptr(o["fpr"]), _ptr(o["f1_infeas"]), _ptr(o["f2_norm"]),
+                _ptr(o["penalty"]), _ptr(o["y"]), _ptr(o["evals"]), _ptr(ws), ws.numel(), ctypes.c_void_p(st))
+        _lib.check(rc, "mpcb_solve_f32")
+        return o
+
+    def evaluate_f32(self, P, U, Y=None, C=None, starts: int = 1):
+        """``evaluate`` with float32 CUDA tensors at the boundary (``mpcb_eval_f32``)."""
+        torch = self._torch
+        d = self.dims
+        n_p = P.shape[0]
+        B = n_p * starts
+        f32 = torch.float32
+        self._chk(P, (n_p, d.np), "P", f32)
+        self._chk(U, (B, d.nu_total), "U", f32)
+        self._chk(Y, (B, d.n1), "Y", f32)
+        self._chk(C, (B,), "C", f32)
+        with torch.cuda.device(self.device):
+            ws = self._workspace_f32(n_p, starts, extra=((B * d.n2 * 8 + 255) // 256) * 256)
+            kf = dict(device=self.device, dtype=f32)
+            out = dict(f=torch.empty(B, **kf), psi=torch.empty(B, **kf), grad=torch.empty(B, d.nu_total, **kf),
+                       F1=torch.empty(B, d.n1, **kf), F2=torch.empty(B, d.n2, **kf))
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            rc = self.lib.mpcb_eval_f32(ctypes.byref(self._cd), ctypes.byref(self._cr), ctypes.byref(self._cc),
+                                        n_p, starts, _ptr(P), _ptr(U), _ptr(Y), _ptr(C), _ptr(out["f"]),
+                                        _ptr(out["psi"]), _ptr(out["grad"]), _ptr(out["F1"]), _ptr(out["F2"]),
+                                        _ptr(ws), ws.numel(), ctypes.c_void_p(st))
+        _lib.check(rc, "mpcb_eval_f32")
+        return out
+
+
 class Solver:
     """Drop-in for the object ``<optimizer_name>.solver()`` returns (one solve per call).
 

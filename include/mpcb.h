@@ -191,6 +191,33 @@ int32_t mpcb_solve_f64(const mpcb_dims* dims, const mpcb_robot* robot,
                        void* stream);
 
 /*
+ * f32 twins: the same two entry points with float32 DEVICE buffers at the boundary.
+ * The arithmetic stays f64 - PANOC's Lipschitz probe perturbs the iterate by 1e-12 and the 1e-6
+ * radius regulariser scales the ellipse terms by up to 1e12, neither of
+ * which single precision can represent - so this is a boundary mode: inputs are widened exactly on
+ * the device, solved by the f64 kernels, results rounded once.  Stated tolerance: the outputs equal
+ * mpcb_solve_f64's on the widened inputs, rounded to float32 (bit for bit); against an f64 solve of
+ * the unrounded parameters the difference is the effect of rounding p to float32 (about 1e-6 m in
+ * the positions), which PANOC carries to <= 1e-3 in u on converging instances (tests/test_f32.py).
+ * Workspace: mpcb_workspace_bytes_f32 (+ 8*B*n2 bytes, rounded up to 256, for mpcb_eval_f32's F2),
+ * 256-byte aligned.  exit_status / n_outer / n_inner / evals stay int32.
+ */
+int32_t mpcb_workspace_bytes_f32(const mpcb_dims* dims, int32_t n_p, int32_t starts, size_t* bytes);
+int32_t mpcb_solve_f32(const mpcb_dims* dims, const mpcb_robot* robot, const mpcb_solver_cfg* cfg,
+                       int32_t n_p, int32_t starts,
+                       const float* p, const float* u0, const float* y0, const float* c0,
+                       float* u_out, float* cost, int32_t* exit_status,
+                       int32_t* n_outer, int32_t* n_inner,
+                       float* fpr, float* f1_infeas, float* f2_norm,
+                       float* penalty, float* y_out, int32_t* evals,
+                       void* workspace, size_t workspace_bytes, void* stream);
+int32_t mpcb_eval_f32(const mpcb_dims* dims, const mpcb_robot* robot, const mpcb_solver_cfg* cfg,
+                      int32_t n_p, int32_t starts,
+                      const float* p, const float* u, const float* y, const float* c,
+                      float* f, float* psi, float* grad, float* F1, float* F2,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Host-buffer convenience for the single-solve path the reference actually
  * uses (one p list per timestep): copies p (and u0 if given) H2D, solves one
  * instance, copies the results back, synchronises.  All pointers are HOST.

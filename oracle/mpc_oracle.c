@@ -601,6 +601,26 @@ typedef struct {
     long n_cost, n_grad, n_small;
 } panoc_t;
 
+/* ---- sensitivity switches (tests/ and scripts/solver_sensitivity.py only) ----------------------
+ * The PANOC/ALM half restates upstream code that is absent from /root/reference and cannot be
+ * built here.  The three details of that restatement most likely to differ from the real
+ * optimization_engine are selectable, so that their effect on the returned status / solution
+ * can be MEASURED instead of guessed (DESIGN.md "Oracle and parity status"):
+ *   akkt  0: as restated - the previous gradient is cached at the top of step(), so the AKKT
+ *            residual reduces to |gamma_fpr| / gamma
+ *         1: no AKKT test at all (exit on |gamma_fpr| < tolerance alone)
+ *         2: the previous gradient is the gradient at the PREVIOUS iterate (cached before the
+ *            line search overwrites it): residual |gamma_fpr/gamma + grad(u_k) - grad(u_{k-1})|
+ *   ls    0: as restated - an exhausted line search keeps its last trial point
+ *         1: an exhausted line search falls back to the plain forward-backward step (tau = 0:
+ *            u <- u_half, cost and gradient re-evaluated there)
+ *   last  0: as restated - NotConvergedIterations whenever the outer-iteration cap was reached
+ *         1: a solve whose exit criterion is met AT the last outer iteration reports the inner
+ *            status (Converged)
+ * Not thread-local: set before a batch, read by every worker. */
+static int g_var_akkt = 0, g_var_ls = 0, g_var_last = 0;
+void mpco_set_variant(int akkt, int ls, int last) { g_var_akkt = akkt; g_var_ls = ls; g_var_last = last; }
+
 static double psi_cost(panoc_t* S, const double* u)
 {
     double psi;
@@ -672,6 +692,7 @@ static void panoc_init(panoc_t* S, double* u)
 static int exit_condition(const panoc_t* S)
 {
     if (!(S->norm_gfpr < S->cfg->tolerance)) return 0;
+    if (g_var_akkt == 1) return 1;
     /* AKKT residual |gfpr/gamma + df - df_prev| (PANOCCache::akkt_residual) */
     double r = 0.0;
     for (int i = 0; i < S->n; ++i) {
@@ -719,7 +740,7 @@ static double sqdiff(const double* a, const double* b, int n)
 static int panoc_step(panoc_t* S, double* u)
 {
     int n = S->n;
-    if (S->iter >= 1) memcpy(S->grad_prev, S->grad, sizeof(double) * (size_t)n);
+    if (S->iter >= 1 && g_var_akkt != 2) memcpy(S->grad_prev, S->grad, sizeof(double) * (size_t)n);
     compute_fpr(S, u);
     if (exit_condition(S)) return 0;
     if (S->norm_gfpr < S->cfg->tolerance) S->n_small++;   /* AKKT test failed: the solve goes on */
@@ -730,6 +751,7 @@ static int panoc_step(panoc_t* S, double* u)
         memcpy(S->dir, S->gfpr, sizeof(double) * (size_t)n);
         lbfgs_apply(&S->lb, S->dir);
     }
+    if (g_var_akkt == 2) memcpy(S->grad_prev, S->grad, sizeof(double) * (size_t)n);   /* grad(u_k), before the update */
     if (S->iter == 0) {
         /* update_no_linesearch */
         memcpy(u, S->u_half, sizeof(double) * (size_t)n);
@@ -762,6 +784,15 @@ static int panoc_step(panoc_t* S, double* u)
         }
         /* upstream: on exhaustion sets tau=0 and u<-u_half, then overwrites
          * u<-u_plus unconditionally: the last trial point is what is kept. */
+        if (g_var_ls == 1 && S->lhs_ls > S->rhs_ls) {
+            /* variant: fall back to the forward-backward step u <- u_half of the iterate the search
+             * started from (tau = 0: u - gfpr), cost and gradient re-evaluated there */
+            for (int i = 0; i < n; ++i) S->u_plus[i] = u[i] - S->gfpr[i];
+            S->cost = psi_cost(S, S->u_plus);
+            psi_grad(S, S->u_plus, S->grad);
+            for (int i = 0; i < n; ++i) S->gstep[i] = S->u_plus[i] - S->gamma * S->grad[i];
+            half_step(S);
+        }
         memcpy(u, S->u_plus, sizeof(double) * (size_t)n);
     }
     S->iter++;
@@ -824,7 +855,7 @@ int32_t mpco_solve(const mpcb_dims* d, const mpcb_robot* rb, const mpcb_solver_c
     double dy = 0.0, dy_plus = 0.0, f2n = 0.0, f2n_plus = 0.0, last_fpr = -1.0;
     int alm_iter = 0, n_outer = 0, inner_total = 0;
     int exit_status = MPCB_CONVERGED;
-    int failed = 0;
+    int failed = 0, met_criterion = 0;
 
     const int budget = cfg->max_inner_total > 0 ? cfg->max_inner_total : 0;
     for (int outer = 1; outer <= cfg->max_outer; ++outer) {
@@ -870,6 +901,7 @@ int32_t mpco_solve(const mpcb_dims* d, const mpcb_robot* rb, const mpcb_solver_c
         int c3 = S->akkt_tol <= cfg->tolerance + EPS;
         if (c1 && c2 && c3) {
             exit_status = inner_status;
+            met_criterion = 1;
             break;
         }
         /* is_penalty_stall_criterion */
@@ -885,7 +917,7 @@ int32_t mpco_solve(const mpcb_dims* d, const mpcb_robot* rb, const mpcb_solver_c
         memcpy(S->y, y_plus, sizeof(double) * (size_t)n1);
         if (outer == cfg->max_outer) exit_status = MPCB_NOT_CONVERGED_ITERATIONS;
     }
-    if (!failed && n_outer == cfg->max_outer) exit_status = MPCB_NOT_CONVERGED_ITERATIONS;
+    if (!failed && n_outer == cfg->max_outer && !(g_var_last == 1 && met_criterion)) exit_status = MPCB_NOT_CONVERGED_ITERATIONS;
 
     double cost = 0.0;
     mpco_eval(d, rb, p, u, 0, 0.0, &cost, 0, 0, 0, 0);

@@ -48,6 +48,12 @@ def lib():
     return _LIB
 
 
+def set_variant(akkt: int = 0, ls: int = 0, last: int = 0):
+    """Sensitivity switches of the reference-order oracle (mpc_oracle.c "sensitivity switches");
+    (0, 0, 0) is the restatement everything else is checked against."""
+    lib().mpco_set_variant(ctypes.c_int(akkt), ctypes.c_int(ls), ctypes.c_int(last))
+
+
 def _p(a):
     return None if a is None else a.ctypes.data_as(_dp)
 

@@ -21,7 +21,11 @@ opengen is installed, so this script installs two tiny stand-ins into
 The unmodified reference files executed are mpc_builder.py, mpc_cost.py,
 mpc_helper.py, motion_model.py (unicycle_model) and configs.py.
 Output: tests/golden/psi_cases.npz  (committed; the tests do not need the
-reference).  Usage:  python tests/golden/gen_golden.py
+reference).
+Usage:  python tests/golden/gen_golden.py                re-run the reference on the COMMITTED inputs and
+                                                         print the largest difference from the committed
+                                                         outputs (0 expected; --write stores them)
+        python tests/golden/gen_golden.py --new-inputs   draw new inputs with the current generator
 """
 import os
 import sys
@@ -312,6 +316,37 @@ def reference_eval(builder_mod, motion_model, cfg_path, dims, feed, Problem, p, 
                 cmin=np.asarray(prob.set_c.xmin), cmax=np.asarray(prob.set_c.xmax))
 
 
+def reevaluate_committed(mpc_builder, motion_model, base_cfg, feed, Problem, write):
+    """The committed INPUTS (p, u, y, c, dims of every case in psi_cases.npz) are the source of truth:
+    run the reference on them again and compare with (or rewrite) the committed outputs.  This is
+    what makes the fixture reproducible whatever happens to the synthetic instance generator."""
+    from dyobav_mpcnwta_warehouse_b200 import Dims
+    path = os.path.join(HERE, "psi_cases.npz")
+    old = dict(np.load(path))
+    worst = 0.0
+    for key in [str(k) for k in old["cases"]]:
+        dims = Dims(*[int(v) for v in old[f"{key}/dims"]])
+        cfgd = dict(base_cfg)
+        cfgd.update(N_hor=dims.N, Nother=dims.Nother, Nstcobs=dims.Nstc, nstcobs=3 * dims.nedge, Ndynobs=dims.Ndyn)
+        with tempfile.NamedTemporaryFile("w", suffix=".yaml", delete=False) as fh:
+            yaml.safe_dump(cfgd, fh)
+            cfg_path = fh.name
+        g = reference_eval(mpc_builder, motion_model, cfg_path, dims, feed, Problem, old[f"{key}/p"],
+                           old[f"{key}/u"], old[f"{key}/y"], float(old[f"{key}/c"]))
+        os.unlink(cfg_path)
+        for k, v in g.items():
+            d = float(np.max(np.abs(np.asarray(v) - old[f"{key}/{k}"]))) if np.size(v) else 0.0
+            worst = max(worst, d)
+            if write:
+                old[f"{key}/{k}"] = np.asarray(v)
+        print(key, "max |reference - committed| over its outputs so far: %.3g" % worst)
+    if write:
+        np.savez_compressed(path, **old)
+        print("rewrote", path)
+    print("MAXDIFF %.17g" % worst)
+    return worst
+
+
 def main():
     from dyobav_mpcnwta_warehouse_b200 import Dims, instances
 
@@ -323,6 +358,12 @@ def main():
 
     with open(os.path.join(REF, "config", "mpc_fast.yaml")) as fh:
         base_cfg = yaml.safe_load(fh)
+
+    if "--new-inputs" not in sys.argv:
+        # default: the reference re-evaluated on the committed inputs (--write stores the outputs)
+        reevaluate_committed(mpc_builder, motion_model, base_cfg, feed, Problem, "--write" in sys.argv)
+        return
+    # --new-inputs: draw fresh inputs with the CURRENT instance generator (changes the fixture)
 
     cases = []
     rng = np.random.default_rng(20231017)

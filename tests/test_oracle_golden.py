@@ -93,12 +93,40 @@ def test_known_answer_refpath_deviation():
 
 
 def test_known_answer_fleet_and_points():
-    # dist_to_points_square p=(0,0) vs (1,0),(2,0) -> [1,4]; cost_fleet_collision p=(1,2), safe 2,
-    # weight 2 vs (0,1),(2,0) -> 4 ; vs (0,0),(2,0) -> 0   (test_mpc_builder.py:16-26,181-200)
-    def fleet(p, pts, safe, w):
-        return w * sum(max(0.0, safe ** 2 - ((p[0] - q[0]) ** 2 + (p[1] - q[1]) ** 2)) for q in pts)
-    assert fleet((1, 2), [(0, 0), (2, 0)], 2, 2) == 0
-    assert fleet((1, 2), [(0, 1), (2, 0)], 2, 2) == 4
+    """cost_fleet_collision p=(1,2), safe distance 2 vs (0,1),(2,0) -> sum of hinges 2 (the reference's
+    test weighs it by 2 -> 4), vs (0,0),(2,0) -> 0 (test_mpc_builder.py:181-200), evaluated by BOTH
+    oracles through the whole problem: a one-step horizon with every other weight zero, the robot at
+    rest at (1,2), the predicted robots `c` at the test's points (weight 10, mpc_builder.py:93-97) and
+    the t=0 robots `c_0` far away."""
+    from dyobav_mpcnwta_warehouse_b200 import Dims, RobotSpec
+    d = Dims(N=1, Nother=3, Nstc=0, nedge=4, Ndyn=0)
+    rb = RobotSpec(vehicle_width=2.0)
+    lay = d.layout()
+    for pts, hinge_sum in (([(0, 1), (2, 0)], 2.0), ([(0, 0), (2, 0)], 0.0)):
+        p = np.zeros(d.np)
+        p[lay["s_0"][0]:lay["s_0"][0] + 3] = [1.0, 2.0, 0.3]
+        p[lay["r_s"][0]:lay["r_s"][0] + 3] = [1.0, 2.0, 0.3]
+        c0 = np.full((d.Nother, 3), 50.0)
+        p[lay["c_0"][0]:lay["c_0"][0] + 9] = c0.reshape(-1)
+        c = np.full((d.Nother, d.N, 3), 50.0)
+        for r, q in enumerate(pts):
+            c[r, 0, :2] = q
+        p[lay["c"][0]:lay["c"][0] + 9] = c.reshape(-1)
+        for laned in (False, True):
+            out = oracle.evaluate(d, rb, p, np.zeros(2), None, 10.0, laned=laned)
+            assert out["f"] == 10.0 * hinge_sum, (pts, laned)
+            # d cost / d v: the hinge is linear in the squared distance (mpc_cost.py:75)
+            assert np.isfinite(out["grad"]).all()
+    # dist_to_points_square p=(0,0) vs (1,0),(2,0) -> [1, 4] (test_mpc_builder.py:16-26): the same
+    # squared distances through the hinge with safe distance^2 = 5: [5-1, 5-4]
+    rb5 = RobotSpec(vehicle_width=math.sqrt(5.0))
+    p = np.zeros(d.np)
+    c = np.full((d.Nother, d.N, 3), 50.0)
+    c[0, 0, :2] = (1, 0); c[1, 0, :2] = (2, 0)
+    p[lay["c"][0]:lay["c"][0] + 9] = c.reshape(-1)
+    p[lay["c_0"][0]:lay["c_0"][0] + 9] = 50.0
+    out = oracle.evaluate(d, rb5, p, np.zeros(2), None, 10.0)
+    assert out["f"] == pytest.approx(10.0 * ((5 - 1) + (5 - 4)), rel=1e-12)
 
 
 def test_unicycle_rk4_matches_closed_form():
@@ -113,3 +141,19 @@ def test_unicycle_rk4_matches_closed_form():
     assert out[0] == pytest.approx(0.3 + cx, abs=1e-15)
     assert out[1] == pytest.approx(-0.2 + sy, abs=1e-15)
     assert out[2] == pytest.approx(th + ts * w, abs=1e-15)
+
+
+def test_committed_goldens_regenerate_from_their_own_inputs():
+    """tests/golden/gen_golden.py re-runs the REFERENCE'S code on the committed inputs: the committed
+    outputs must come back exactly (authoring container only: needs /root/reference)."""
+    import os
+    import subprocess
+    import sys
+    if not os.path.isdir("/root/reference/src"):
+        pytest.skip("the reference tree is only present in the authoring container")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, os.path.join(here, "golden", "gen_golden.py")], capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("MAXDIFF")][-1]
+    assert float(line.split()[1]) == 0.0, line
