@@ -148,6 +148,69 @@ class ClosedLoopBatch:
                 break
 
 
+# ---------------------------------------------------------------------------------------------
+# Episode metrics of the evaluation loop (main_eva.py: main_base.py:327-336,426-434; main_pre.py:20-53)
+def point_polygon_distance(pt, poly) -> float:
+    """Distance from a point to a convex polygon, 0 inside (shapely's ``Polygon.distance(Point)``)."""
+    V = np.asarray(poly, dtype=np.float64)
+    m = V.shape[0]
+    sg, inside, best = 0, True, math.inf
+    for i in range(m):
+        x0, y0 = V[i]
+        x1, y1 = V[(i + 1) % m]
+        dx, dy = x1 - x0, y1 - y0
+        cr = dx * (pt[1] - y0) - dy * (pt[0] - x0)
+        if cr == 0:
+            inside = False
+        elif sg == 0:
+            sg = 1 if cr > 0 else -1
+        elif (cr > 0) != (sg > 0):
+            inside = False
+        t = min(1.0, max(0.0, ((pt[0] - x0) * dx + (pt[1] - y0) * dy) / (dx * dx + dy * dy)))
+        best = min(best, math.hypot(x0 + t * dx - pt[0], y0 + t * dy - pt[1]))
+    return 0.0 if inside else best
+
+
+def check_collision(state, polygons, pedestrians, human_size: float = 0.2) -> bool:
+    """``check_collision`` (main_pre.py:20-31): strictly inside an (inflated) polygon, or within a
+    pedestrian's radius."""
+    if any(point_polygon_distance(state, p) == 0.0 and _strictly_inside(state, p) for p in polygons):
+        return True
+    return any(math.hypot(state[0] - q[0], state[1] - q[1]) <= human_size for q in pedestrians)
+
+
+def _strictly_inside(pt, poly) -> bool:
+    V = np.asarray(poly, dtype=np.float64)
+    m = V.shape[0]
+    sg = 0
+    for i in range(m):
+        x0, y0 = V[i]
+        x1, y1 = V[(i + 1) % m]
+        cr = (x1 - x0) * (pt[1] - y0) - (y1 - y0) * (pt[0] - x0)
+        if cr == 0:
+            return False
+        if sg == 0:
+            sg = 1 if cr > 0 else -1
+        elif (cr > 0) != (sg > 0):
+            return False
+    return True
+
+
+def episode_metrics(actions, trajectory, ref_traj, polygons, dyn_clearances):
+    """The four evaluation metrics of a finished episode (main_base.py:426-434):
+    smoothness = mean |second difference| of the speeds / angular speeds (main_pre.py:33-36),
+    clearance = smallest distance of the driven positions to the inflated polygons (:38-42),
+    deviation = [mean, max] distance of the driven positions to the reference trajectory (:48-52),
+    dynamic clearance = smallest per-step distance to a pedestrian (:44-46, main_base.py:329)."""
+    import statistics
+    a = np.asarray(actions, dtype=np.float64)
+    smooth = [statistics.mean(np.abs(np.diff(a[:, 0], n=2))), statistics.mean(np.abs(np.diff(a[:, 1], n=2)))]
+    clearance = min(min(point_polygon_distance(pos, ob) for ob in polygons) for pos in trajectory)
+    dev = [min(math.hypot(r[0] - pos[0], r[1] - pos[1]) for r in ref_traj) for pos in trajectory]
+    return dict(smoothness=smooth, clearance=clearance, deviation=[statistics.mean(dev), max(dev)],
+                clearance_dyn=min(dyn_clearances))
+
+
 def make_episodes(n: int, seed: int, n_ped: int = 2, n_modes: int = 3) -> List[Episode]:
     """Small synthetic warehouse episodes: an L-shaped route, two rectangles beside it,
     pedestrians crossing ahead."""

