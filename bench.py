@@ -308,6 +308,7 @@ def main():
         def step_resident():
             solver.run_batch(P_d, U0_d, starts=starts, out=out)
 
+        solver._workspace(hi - lo, starts)                    # sized once, outside every timed region
         for _ in range(warmup):
             if warm_scenarios and warm_scenarios < hi - lo:
                 solver.run_batch(P_d[:warm_scenarios], U0_d[:warm_scenarios * starts], starts=starts)
