@@ -246,6 +246,68 @@ __global__ void __launch_bounds__(128) stage_kernel(const KParams P, const doubl
             }
             MG[L.f_poly + i] = margin_f(m, 0.0);
         }
+        // bounding box of every polygon (position-based culling: the indicator is a product of
+        // max(0, half-plane value), exactly zero outside the polygon).  Vertices = feasible pairwise
+        // intersections of the edge lines; an unbounded polygon (normals that do not positively span
+        // the plane) gets an infinite box, a zero-row slot an empty one.
+        for (int pl = tid; pl < L.Nstc; pl += nt) {
+            const double* q = pr + L.p_os + pl * 3 * L.nedge;
+            const float PINF = __int_as_float(0x7f800000);
+            float bx[4] = {PINF, -PINF, PINF, -PINF};           // empty
+            bool zero_row = false, bad = false;
+            double ang[MPCB_MAX_EDGE];
+            bool real[MPCB_MAX_EDGE];          // a genuine half-plane (a constant row b > 0 is only a factor)
+            int nreal = 0;
+            for (int e = 0; e < L.nedge; ++e) {
+                const double a0 = q[L.nedge + e], a1 = q[2 * L.nedge + e], b = q[e];
+                bad |= !(a0 == a0) || !(a1 == a1) || !(b == b);
+                real[e] = !(a0 == 0.0 && a1 == 0.0);
+                if (!real[e] && b <= 0.0) zero_row = true;                 // this edge is never positive
+                nreal += real[e];
+                ang[e] = atan2(a1, a0);
+            }
+            bool bounded = !bad && nreal >= 3;
+            if (bounded && !zero_row) {
+                // largest angular gap between consecutive outward normals must be < pi
+                for (int e = 0; e < L.nedge && bounded; ++e) {
+                    if (!real[e]) continue;
+                    double gap = 7.0;
+                    for (int f = 0; f < L.nedge; ++f) {
+                        if (f == e || !real[f]) continue;
+                        double d = ang[f] - ang[e];
+                        while (d <= 0.0) d += 6.283185307179586;
+                        gap = d < gap ? d : gap;
+                    }
+                    if (gap >= 3.141592653589793 - 1e-9) bounded = false;
+                }
+                if (bounded) {
+                    int nv = 0;
+                    for (int e = 0; e < L.nedge; ++e)
+                        for (int f = e + 1; f < L.nedge; ++f) {
+                            const double a0 = q[L.nedge + e], a1 = q[2 * L.nedge + e], b = q[e];
+                            const double c0 = q[L.nedge + f], c1 = q[2 * L.nedge + f], d = q[f];
+                            const double det = a0 * c1 - a1 * c0;
+                            if (fabs(det) < 1e-14 * (fabs(a0 * c1) + fabs(a1 * c0)) || det == 0.0) continue;
+                            const double vx = (b * c1 - a1 * d) / det, vy = (a0 * d - b * c0) / det;
+                            bool feas = true;
+                            for (int g = 0; g < L.nedge; ++g) {
+                                const double r = q[g] - q[L.nedge + g] * vx - q[2 * L.nedge + g] * vy;
+                                const double sc_ = fabs(q[g]) + fabs(q[L.nedge + g] * vx) + fabs(q[2 * L.nedge + g] * vy);
+                                if (r < -1e-9 * sc_ - 1e-12) feas = false;
+                            }
+                            if (!feas) continue;
+                            ++nv;
+                            const double mx = 1e-6 + 1e-9 * fabs(vx), my = 1e-6 + 1e-9 * fabs(vy);
+                            bx[0] = fminf(bx[0], __double2float_rd(vx - mx)); bx[1] = fmaxf(bx[1], __double2float_ru(vx + mx));
+                            bx[2] = fminf(bx[2], __double2float_rd(vy - my)); bx[3] = fmaxf(bx[3], __double2float_ru(vy + my));
+                        }
+                    if (nv < 3) bounded = false;
+                }
+            }
+            if (!zero_row && !bounded) { bx[0] = -PINF; bx[1] = PINF; bx[2] = -PINF; bx[3] = PINF; }   // never culled
+            float* o = MG + L.f_pbx + 4 * pl;
+            o[0] = bx[0]; o[1] = bx[1]; o[2] = bx[2]; o[3] = bx[3];
+        }
         // reference path: (k, i) -> min over segments i' >= i of dist(A_k, segment i')
         for (int k = tid; k < N; k += nt) {
             const double ax = sg[k], ay = sg[N + k];

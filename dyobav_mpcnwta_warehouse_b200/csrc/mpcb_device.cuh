@@ -59,6 +59,9 @@ struct Lay {            // offsets (in doubles) inside one staged scenario block
     int f_seg2;         // [N][N]: (k, i) -> min over segments i' >= i of (x - A_k).t_k, x on the segment,
                         // t_k the (slightly shortened) unit tangent of segment k: a directional bound
     int f_bx0;          // [Ndyn][4]: bounding box (xmin, xmax, ymin, ymax) of the inflated t = 0 ellipse
+    int f_pbx;          // [Nstc][4]: bounding box (xmin, xmax, ymin, ymax) of a bounded polygon (outside it the
+                        // polygon indicator is exactly zero); (-inf, inf, ...) for an unbounded one, empty for
+                        // a zero-row (unused) slot
     int f_bx1;          // [Ndyn][NB][4]: bounding box of the inflated t = k+1 ellipses of the steps of block b
                         // (blocks of 8 steps, NB = ceil(N/8)); both 16-byte aligned, rounded outwards
     int total;          // doubles, multiple of 2 (16-byte granularity for TMA bulk copies)
@@ -112,6 +115,7 @@ __host__ __device__ constexpr Lay make_lay(int N, int Nother, int Nstc, int nedg
     while ((2 * L.o_mg + fo) & 3) ++fo;          // float4 loads
     L.f_bx0 = fo;  fo += 4 * Ndyn;
     L.f_bx1 = fo;  fo += 4 * Ndyn * ((N + 7) / 8);
+    L.f_pbx = fo;  fo += 4 * Nstc;
     o += (fo + 1) / 2;
     L.total = (o + 1) & ~1;
     int q = 0;
@@ -157,7 +161,7 @@ struct LayV {
     MPCB_LAYF(N) MPCB_LAYF(Nother) MPCB_LAYF(Nstc) MPCB_LAYF(nedge) MPCB_LAYF(Ndyn)
     MPCB_LAYF(o_hdr) MPCB_LAYF(o_rv) MPCB_LAYF(o_qstc) MPCB_LAYF(o_seg) MPCB_LAYF(o_c0) MPCB_LAYF(o_c)
     MPCB_LAYF(o_poly) MPCB_LAYF(o_e0) MPCB_LAYF(o_et) MPCB_LAYF(o_mg)
-    MPCB_LAYF(f_e0) MPCB_LAYF(f_et) MPCB_LAYF(f_poly) MPCB_LAYF(f_c0) MPCB_LAYF(f_c) MPCB_LAYF(f_imin) MPCB_LAYF(f_seg) MPCB_LAYF(f_seg2) MPCB_LAYF(f_bx0) MPCB_LAYF(f_bx1)
+    MPCB_LAYF(f_e0) MPCB_LAYF(f_et) MPCB_LAYF(f_poly) MPCB_LAYF(f_c0) MPCB_LAYF(f_c) MPCB_LAYF(f_imin) MPCB_LAYF(f_seg) MPCB_LAYF(f_seg2) MPCB_LAYF(f_bx0) MPCB_LAYF(f_bx1) MPCB_LAYF(f_pbx)
     MPCB_LAYF(total)
 #undef MPCB_LAYF
 };
@@ -193,6 +197,10 @@ struct LayV {
 // box) culling of the ellipses instead of the anchor-based margins
 #ifndef MPCB_BOX_CULL
 #define MPCB_BOX_CULL(FIXED) ((FIXED) != 1)
+#endif
+// polygons: test the robot's position against the polygon's bounding box instead of the anchor margin
+#ifndef MPCB_POLY_BOX
+#define MPCB_POLY_BOX 1
 #endif
 #ifndef MPCB_TEAM_SOLVERS
 #define MPCB_TEAM_SOLVERS 2
@@ -766,7 +774,13 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
                 while (mk) {
                     const int i = base + __ffs(mk) - 1;
                     mk &= mk - 1;
-                    if (mp[i * N] > D) continue;
+                    if (MPCB_POLY_BOX) {
+                        // position test: outside the polygon's bounding box the indicator is exactly 0
+                        const float4 qb = reinterpret_cast<const float4*>(MG + L.f_pbx())[i];
+                        const float xf_lo = __double2float_rd(x), xf_hi = __double2float_ru(x);
+                        const float yf_lo = __double2float_rd(y), yf_hi = __double2float_ru(y);
+                        if (CULL && (xf_hi < qb.x || xf_lo > qb.y || yf_hi < qb.z || yf_lo > qb.w)) continue;
+                    } else if (mp[i * N] > D) continue;
                     double dIx, dIy;
                     const double I = polygon_ind(GRAD, pe + i * 3 * L.nedge(), L.nedge(), x, y, dIx, dIy);
                     if (I > 0.0) {
