@@ -17,7 +17,7 @@ ERRORS = {-1: "unsupported or inconsistent dimensions", -2: "required pointer is
 
 # every symbol include/mpcb.h declares
 EXPORTS = ("mpcb_abi_version", "mpcb_last_error", "mpcb_param_len", "mpcb_num_decision", "mpcb_n1",
-           "mpcb_n2", "mpcb_team_groups", "mpcb_default_robot", "mpcb_default_solver_cfg", "mpcb_workspace_bytes",
+           "mpcb_n2", "mpcb_team_groups", "mpcb_team_groups_cfg", "mpcb_default_robot", "mpcb_default_solver_cfg", "mpcb_workspace_bytes",
            "mpcb_eval_f64", "mpcb_solve_f64", "mpcb_workspace_bytes_f32", "mpcb_eval_f32", "mpcb_solve_f32",
            "mpcb_solve_one_host", "mpcb_pack_f64",
            "mpcb_plant_step_f64", "mpcb_sincos_host", "mpcb_cluster_f64", "mpcb_fp64_peak_tflops")
@@ -49,6 +49,8 @@ def load():
     for name in ("mpcb_param_len", "mpcb_num_decision", "mpcb_n1", "mpcb_n2", "mpcb_team_groups"):
         getattr(L, name).restype = i32
         getattr(L, name).argtypes = [pd]
+    L.mpcb_team_groups_cfg.restype = i32
+    L.mpcb_team_groups_cfg.argtypes = [pd, pc]
     L.mpcb_default_robot.argtypes = [pr]
     L.mpcb_default_solver_cfg.argtypes = [pc]
     L.mpcb_workspace_bytes.restype = i32

@@ -727,7 +727,8 @@ int make_plan(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solver_cfg* c,
     if (B > 0x7fffffffLL / (2 * d->N)) return MPCB_E_DIMS;
     P.B = (int)B;
     pl.spl = d->N <= 32 ? 1 : 2;
-    pl.team = team_groups(d->N, d->Ndyn);
+    pl.team = team_groups(d->N, d->Ndyn, c->team_mode == 1);
+    P.team_G = pl.team;
     const int M = c->lbfgs_mem + 1;
     // per-warp scratch: L-BFGS rows + rho/alpha, then y, y+ and the parked solver state
     P.lb_doubles = need_lbfgs ? (((2 * M * 2 * d->N + 2 * M + 1) & ~1) + scratch_doubles(d->N)) : 0;
@@ -835,6 +836,10 @@ int32_t mpcb_num_decision(const mpcb_dims* d) { return d ? 2 * d->N : -1; }
 int32_t mpcb_n1(const mpcb_dims* d) { return d ? 2 * d->N : -1; }
 int32_t mpcb_n2(const mpcb_dims* d) { return d ? (d->Ndyn > 0 ? d->Ndyn : 1) : -1; }
 int32_t mpcb_team_groups(const mpcb_dims* d) { return d ? team_groups(d->N, d->Ndyn) : -1; }
+int32_t mpcb_team_groups_cfg(const mpcb_dims* d, const mpcb_solver_cfg* c)
+{
+    return d && c ? team_groups(d->N, d->Ndyn, c->team_mode == 1) : -1;
+}
 
 void mpcb_default_robot(mpcb_robot* r)
 {
@@ -850,6 +855,7 @@ void mpcb_default_solver_cfg(mpcb_solver_cfg* c)
     c->inner_tol_update = 0.1; c->penalty_update = 5.0; c->sufficient_decrease = 0.1;
     c->initial_penalty = 10.0; c->sy_epsilon = 1e-10; c->cbfgs_epsilon = 1e-8; c->cbfgs_alpha = 1.0;
     c->max_inner = 500; c->max_outer = 10; c->lbfgs_mem = 10; c->max_inner_total = 0;
+    c->team_mode = 0; c->reserved = 0;
 }
 
 int32_t mpcb_workspace_bytes(const mpcb_dims* d, int32_t n_p, int32_t starts, size_t* bytes)

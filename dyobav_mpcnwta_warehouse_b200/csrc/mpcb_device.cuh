@@ -83,6 +83,7 @@ struct KParams {
     int budget;          // > 0: cap on the inner iterations of one solve (cfg->max_inner_total)
     unsigned long long* prof;   // launch profile in the workspace header (nullable): [CTAS] start, [CTAS][WARPS] finish
     const int* order;           // queue slot -> scenario, hardest first (nullable: identity)
+    int team_G;                 // worker groups of the team kernels for this launch (0: one-warp kernels)
 };
 #include "../../include/mpcb.h"     // MPCB_WS_PROF_CTAS / MPCB_WS_PROF_WARPS
 
@@ -225,9 +226,9 @@ constexpr int TEAM_WORKERS = TEAM_THREADS - 32 * TEAM_NS;      // worker threads
 #define MPCB_TEAM_CTAS (12 / MPCB_TEAM_WARPS)     // resident teams per SM the register budget is cut for
 #endif
 // number of worker groups (a power of two <= 32 with G*N <= worker threads); 0: one-warp kernel
-__host__ __device__ constexpr int team_groups(int N, int Ndyn)
+__host__ __device__ constexpr int team_groups(int N, int Ndyn, bool force = false)
 {
-    if (Ndyn < MPCB_TEAM_MIN_NDYN) return 0;
+    if (Ndyn < MPCB_TEAM_MIN_NDYN && !force) return 0;
     int g = 1;
     while (2 * g <= 32 && 2 * g * N <= TEAM_WORKERS) g *= 2;
     return g;
@@ -1114,7 +1115,7 @@ __device__ __forceinline__ void team_worker(const KParams& P, double* solvers, i
 {
     const LayV<FIXED> L{&P.L};
     const int N = L.N(), Ndyn = L.Ndyn();
-    const int G = team_groups(N, Ndyn);
+    const int G = FIXED != 0 ? team_groups(N, Ndyn) : P.team_G;   // (run-time dims: may be the forced latency mode)
     double* const PART = reinterpret_cast<double*>(pool) + 2;
     double* const PB = PART + 6 * G * N;
     int* const PI = reinterpret_cast<int*>(PB + G * N);

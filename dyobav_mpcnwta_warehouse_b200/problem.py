@@ -50,7 +50,8 @@ class CSolverCfg(ctypes.Structure):
         "penalty_update", "sufficient_decrease", "initial_penalty", "sy_epsilon",
         "cbfgs_epsilon", "cbfgs_alpha")] + [
         ("max_inner", ctypes.c_int32), ("max_outer", ctypes.c_int32),
-        ("lbfgs_mem", ctypes.c_int32), ("max_inner_total", ctypes.c_int32)]
+        ("lbfgs_mem", ctypes.c_int32), ("max_inner_total", ctypes.c_int32),
+        ("team_mode", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 @dataclass(frozen=True)
@@ -141,6 +142,12 @@ class SolverSettings:
     # 0 = off.  Budget on the inner iterations of one solve, the batch analogue of the reference's
     # wall-clock cap ``max_solver_time`` (mpc_fast.yaml:45): exhausted -> "NotConvergedOutOfTime"
     max_inner_total: int = 0
+    # 0 = kernels chosen by the dimensions (team kernels from 64 ellipses on); 1 = team kernels for any
+    # dimensions (one instance gets a solver warp plus the worker pool of a CTA instead of one warp).
+    # Selects the team arithmetic contract, so results differ from mode 0 by round-off; both are mirrored
+    # by the laned oracle.  Meant as a latency mode for single solves; measured on B200 it only pays when
+    # the per-step part of an evaluation is large (for the reference's dims it is 1.4x SLOWER).
+    team_mode: int = 0
 
     def __post_init__(self):
         if not (1 <= self.lbfgs_mem <= MAX_LBFGS):
@@ -151,7 +158,7 @@ class SolverSettings:
                           self.inner_tol_update, self.penalty_update,
                           self.sufficient_decrease, self.initial_penalty, self.sy_epsilon,
                           self.cbfgs_epsilon, self.cbfgs_alpha, self.max_inner,
-                          self.max_outer, self.lbfgs_mem, int(self.max_inner_total))
+                          self.max_outer, self.lbfgs_mem, int(self.max_inner_total), int(self.team_mode), 0)
 
 
 # The yaml keys of config/mpc_fast.yaml / mpc_default.yaml with their shipped

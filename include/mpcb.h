@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MPCB_ABI_VERSION 2
+#define MPCB_ABI_VERSION 3
 
 /* ---- error codes --------------------------------------------------------- */
 #define MPCB_OK            0
@@ -97,6 +97,14 @@ typedef struct mpcb_solver_cfg {
                                   * NotConvergedOutOfTime), the ALM step finishes as usual and the
                                   * next outer iteration is refused with MPCB_NOT_CONVERGED_OUT_OF_TIME,
                                   * the status mpc_fast.yaml:48 lists in bad_exit_codes.             */
+    int32_t team_mode;           /* 0 = by the dimensions (team kernels from 64 ellipses on), 1 = team
+                                  * kernels for ANY dimensions - one instance gets a whole CTA (a solver
+                                  * warp plus the worker pool) instead of one warp.  Selects the team
+                                  * arithmetic contract (mpcb_team_groups_cfg), so results differ from
+                                  * team_mode 0 by round-off.  Meant as a latency mode for single solves;
+                                  * measured on B200 it pays only when the per-step part of an evaluation
+                                  * is large (reference dims: 28.7 vs 20.8 us per inner iteration).     */
+    int32_t reserved;
 } mpcb_solver_cfg;
 
 #define MPCB_MAX_LBFGS 10
@@ -115,6 +123,8 @@ int32_t mpcb_n2(const mpcb_dims* dims);
  * the arithmetic contract: with G > 0 the ellipse cost terms of a horizon step are summed per
  * group i % G first (csrc/mpcb_device.cuh "team mode"); the laned oracle mirrors the rule. */
 int32_t mpcb_team_groups(const mpcb_dims* dims);
+/* ... and with cfg->team_mode taken into account (what mpcb_solve / mpcb_eval will really use). */
+int32_t mpcb_team_groups_cfg(const mpcb_dims* dims, const mpcb_solver_cfg* cfg);
 
 int32_t mpcb_abi_version(void);
 /* Text of the last CUDA error seen by this thread ("" if none). */

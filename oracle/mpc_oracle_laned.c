@@ -164,6 +164,19 @@ static double dotw(int J, lanes_t a0, lanes_t a1, lanes_t b0, lanes_t b1)
  * +0.0), the group sums are added together in group order (from +0.0) and the total is added to
  * the step's accumulators; the F2 share of the gradient adds both slots of an ellipse before the
  * fma. */
+static __thread int g_force_team = 0;     /* cfg->team_mode == 1 (set per call), or mpcl_set_team_mode for mpcl_eval */
+static int g_force_team_global = 0;
+void mpcl_set_team_mode(int on) { g_force_team_global = on; }
+
+static int team_groups_for(const mpcb_dims* d, int force)
+{
+    if (d->Ndyn < 64 && !force) return 0;
+    int g = 1;
+    while (2 * g <= 32 && 2 * g * d->N <= 32 * 10) g *= 2;
+    return g;
+}
+int32_t mpcl_team_groups_cfg(const mpcb_dims* d, const mpcb_solver_cfg* c) { return team_groups_for(d, c && c->team_mode == 1); }
+
 int32_t mpcl_team_groups(const mpcb_dims* d)
 {
     if (d->Ndyn < 64) return 0;
@@ -184,7 +197,7 @@ static int scen_stage(scen_t* S, const mpcb_dims* d, const mpcb_robot* rb, const
     if (N < 1 || N > MAXN || d->nedge < 1 || d->nedge > MPCB_MAX_EDGE) return MPCB_E_DIMS;
     S->N = N; S->J = N <= W ? 1 : 2;
     S->Nother = d->Nother; S->Nstc = d->Nstc; S->nedge = d->nedge; S->Ndyn = d->Ndyn;
-    S->G = mpcl_team_groups(d);
+    S->G = team_groups_for(d, g_force_team || g_force_team_global);
     S->ts = rb->ts; S->k6 = rb->ts / 6.0; S->inv_ts = 1.0 / rb->ts;
     S->ds2 = rb->vehicle_width * rb->vehicle_width;
     S->vmargin = rb->vehicle_margin; S->smargin = rb->social_margin;
@@ -936,7 +949,9 @@ int32_t mpcl_solve(const mpcb_dims* d, const mpcb_robot* rb, const mpcb_solver_c
 {
     if (!d || !rb || !cfg || !p || !u_out) return MPCB_E_NULL;
     scen_t Sc;
+    g_force_team = cfg->team_mode == 1;
     int rc = scen_stage(&Sc, d, rb, p);
+    g_force_team = 0;
     if (rc) return rc;
     const scen_t* S = &Sc;
     const int N = S->N, J = S->J;

@@ -36,6 +36,7 @@ def lib():
         L.mpcl_solve.restype = ctypes.c_int32
         L.mpcl_solve_batch.restype = ctypes.c_int32
         L.mpcl_team_groups.restype = ctypes.c_int32
+        L.mpcl_team_groups_cfg.restype = ctypes.c_int32
         for f in (L.mpco_dist_to_lineseg, L.mpco_inside_ellipse, L.mpco_inside_cvx_polygon):
             f.restype = ctypes.c_double
         L.mpco_dist_to_lineseg.argtypes = [ctypes.c_double] * 6
@@ -62,9 +63,11 @@ def _c(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
 
 
-def evaluate(dims, robot, p, u, y=None, c=10.0, want_grad=True, laned=False):
-    """f, psi, grad psi, F1, F2 for one instance (laned=True: the kernel's operation order)."""
+def evaluate(dims, robot, p, u, y=None, c=10.0, want_grad=True, laned=False, team=False):
+    """f, psi, grad psi, F1, F2 for one instance (laned=True: the kernel's operation order;
+    team=True: the team contract forced, as cfg.team_mode = 1 does for the kernels)."""
     L = lib()
+    L.mpcl_set_team_mode(ctypes.c_int(1 if team else 0))
     fn = L.mpcl_eval if laned else L.mpco_eval
     cd, cr = dims.to_c(), robot.to_c()
     p, u, y = _c(p), _c(u), _c(y)
@@ -76,6 +79,7 @@ def evaluate(dims, robot, p, u, y=None, c=10.0, want_grad=True, laned=False):
     F2 = np.zeros(dims.n2)
     rc = fn(ctypes.byref(cd), ctypes.byref(cr), _p(p), _p(u), _p(y),
                      ctypes.c_double(c), ctypes.byref(f), ctypes.byref(psi), _p(g), _p(F1), _p(F2))
+    L.mpcl_set_team_mode(ctypes.c_int(0))
     if rc:
         raise RuntimeError(f"mpco_eval failed: {rc}")
     return dict(f=f.value, psi=psi.value, grad=g, F1=F1, F2=F2)

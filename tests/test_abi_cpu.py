@@ -18,7 +18,7 @@ def test_header_symbols_all_exported(cuda_solver_lib):
     assert declared == set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(cuda_solver_lib, name), name
-    assert cuda_solver_lib.mpcb_abi_version() == 2
+    assert cuda_solver_lib.mpcb_abi_version() == 3
 
 
 def test_param_len_matches_reference_layout(cuda_solver_lib):
@@ -73,6 +73,17 @@ def test_team_rule_is_the_same_in_library_and_oracle(cuda_solver_lib):
     assert cuda_solver_lib.mpcb_team_groups(ctypes.byref(Dims().to_c())) == 0
     assert cuda_solver_lib.mpcb_team_groups(ctypes.byref(Dims(Ndyn=40).to_c())) == 0
     assert cuda_solver_lib.mpcb_team_groups(ctypes.byref(Dims(N=40, Ndyn=160).to_c())) == 8
+    # latency mode (cfg.team_mode = 1): team kernels for any dimensions, same rule in both
+    from dyobav_mpcnwta_warehouse_b200 import SolverSettings as SS
+    cfg = SS(team_mode=1).to_c()
+    cuda_solver_lib.mpcb_team_groups_cfg.restype = ctypes.c_int32
+    for N in (1, 7, 20, 33, 64):
+        for Ndyn in (0, 15, 40, 160):
+            cd = Dims(N=N, Ndyn=Ndyn).to_c()
+            g = cuda_solver_lib.mpcb_team_groups_cfg(ctypes.byref(cd), ctypes.byref(cfg))
+            assert g > 0 and g == OL.mpcl_team_groups_cfg(ctypes.byref(cd), ctypes.byref(cfg)), (N, Ndyn)
+    assert cuda_solver_lib.mpcb_team_groups_cfg(ctypes.byref(Dims().to_c()), ctypes.byref(cfg)) == 16
+    assert cuda_solver_lib.mpcb_team_groups_cfg(ctypes.byref(Dims().to_c()), ctypes.byref(SS().to_c())) == 0
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
