@@ -552,6 +552,34 @@ __global__ void __launch_bounds__(qthreads(FIXED), MPCB_MIN_CTAS) solve_kernel_q
     solve_worker<SPL, 1, FIXED>(P, nullptr, staged, counter, lb, 0, lane, io);
 }
 
+// K1 (latency variant, small batches): one CTA per instance, warp 0 solves, the helper warps evaluate
+// the line-search trials concurrently (mpcb_solver.cuh "speculative line search").  Same bits as the
+// queue kernel.
+template <int SPL, int FIXED>
+__global__ void __launch_bounds__(SPEC_THREADS, 2) solve_kernel_spec(const KParams P, const double* __restrict__ staged,
+                                                                     const SolveIO io, int* __restrict__ counter)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* lb = reinterpret_cast<double*>(smem_raw);
+    SpecShared* SP = reinterpret_cast<SpecShared*>(lb + P.lb_doubles);
+    int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0 && P.prof) {
+        unsigned long long tns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
+        P.prof[blockIdx.x & (MPCB_WS_PROF_CTAS - 1)] = tns;
+    }
+    if (warp == 0) {
+        asm volatile("" : "+r"(lane));
+        solve_worker<SPL, 1, FIXED, false, true>(P, nullptr, staged, counter, lb, 0, lane, io, nullptr, SP);
+        if (lane == 0) SP->cmd = 0;
+        __syncwarp();
+        bar_sync(1, SPEC_THREADS);
+    } else {
+        spec_helper<SPL, FIXED>(P, SP, warp - 1, lane);
+    }
+}
+
 // K1 (team variant, dimension sets with many ellipses): TEAM_NS solver warps per CTA, each running
 // the solve of one instance (same code as the queue kernel, one queue per CTA), share the worker
 // warps, which evaluate the per-step part of every horizon evaluation (mpcb_device.cuh "team mode").
@@ -694,6 +722,7 @@ struct Plan {
     bool smem;
     int fixed;     // compiled-in dimension set (0: run-time dims)
     int team;      // worker groups of the team kernels (0: one-warp kernels)
+    bool spec;     // latency kernel (speculative line search) for small batches
     int spl;
     size_t smem_bytes;
 };
@@ -773,6 +802,9 @@ int make_plan(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solver_cfg* c,
         while (P.warps > 1 && 16 + P.warps * lbw > cap) --P.warps;   // large N: fewer warps per CTA
         pl.smem_bytes = 16 + P.warps * lbw;
     }
+    // small batches (at most two instances per SM): the latency kernel, same bits as the queue kernel
+    pl.spec = need_lbfgs && !pl.team && !pl.smem && B <= 2 * 148 && env_int("MPCB_SPEC", 1) != 0;
+    if (pl.spec) pl.smem_bytes = (size_t)(P.lb_doubles + spec_doubles(d->N)) * 8;
     if (pl.team) {
         // per solver warp its scratch and its team block, then the worker pool's scratch; the
         // evaluation kernel has one solver and no solver scratch
@@ -978,10 +1010,22 @@ int32_t mpcb_solve_f64(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solve
         if (grid > (int)(WS_COUNTERS / sizeof(int))) grid = (int)(WS_COUNTERS / sizeof(int));      \
         solve_kernel_team<SPL, MD><<<grid, TEAM_THREADS, pl.smem_bytes, st>>>(pl.P, staged, io, counter); \
     } while (0)
+#define LAUNCH_SPEC(SPL, MD)                                                                       \
+    do {                                                                                           \
+        rc = set_smem(solve_kernel_spec<SPL, MD>, pl.smem_bytes);                                  \
+        if (rc) return rc;                                                                         \
+        int grid = pl.P.B < 2 * sms ? pl.P.B : 2 * sms;                                            \
+        solve_kernel_spec<SPL, MD><<<grid, SPEC_THREADS, pl.smem_bytes, st>>>(pl.P, staged, io, counter); \
+    } while (0)
     if (pl.team) {
         if (pl.fixed == 3) LAUNCH_TEAM(2, 3);
         else if (pl.spl == 1) LAUNCH_TEAM(1, 0);
         else LAUNCH_TEAM(2, 0);
+    }
+    else if (pl.spec) {
+        if (pl.fixed == 1) LAUNCH_SPEC(1, 1);
+        else if (pl.spl == 1) LAUNCH_SPEC(1, 0);
+        else LAUNCH_SPEC(2, 0);
     }
     else if (pl.smem) { if (pl.spl == 1) LAUNCH_SOLVE(1, true); else LAUNCH_SOLVE(2, true); }
     else {
@@ -993,6 +1037,7 @@ int32_t mpcb_solve_f64(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solve
 #undef LAUNCH_SOLVE
 #undef LAUNCH_QUEUE
 #undef LAUNCH_TEAM
+#undef LAUNCH_SPEC
     CUDA_TRY(cudaGetLastError());
     return MPCB_OK;
 }

@@ -216,6 +216,94 @@ struct SolveIO {
     double* fpr; double* f1_infeas; double* f2_norm; double* penalty; double* y_out; int32_t* evals;
 };
 
+// ---------------------------------------------------------------- speculative line search
+// LATENCY kernel for small batches (at most two instances per SM): one CTA per instance, warp 0 runs
+// the solve as ever, SPEC_TRIALS helper warps evaluate the line-search trial points tau = 1, 1/2,
+// 1/4, ... CONCURRENTLY instead of one after the other.  PANOC's line search accepts the first trial
+// that passes the envelope test; on this problem it backtracks often (2.7 cost+gradient evaluations
+// per iteration on average), and every evaluation is a dependent chain that one warp cannot overlap.
+// Each trial is the same arithmetic whichever warp runs it, so results, statuses and the evaluation
+// counters (only the trials up to the accepted one are counted) stay bit-identical to the one-warp
+// kernel and to the laned oracle.
+#ifndef MPCB_SPEC_TRIALS
+#define MPCB_SPEC_TRIALS 4
+#endif
+constexpr int SPEC_THREADS = 32 * (1 + MPCB_SPEC_TRIALS);
+struct alignas(16) SpecShared {
+    const double* S;
+    double gamma, ceff;
+    int cmd, ls0, pad0, pad1;
+    double lhs[MPCB_SPEC_TRIALS], cost[MPCB_SPEC_TRIALS], cost_h[MPCB_SPEC_TRIALS];
+};
+// doubles: header, request vectors [8][N] (u0,u1,r0,r1,d0,d1,ya,yw), results [TRIALS][6][N] (pt0,pt1,g0,g1,h0,h1)
+__host__ __device__ constexpr int spec_doubles(int N)
+{
+    return (int)(sizeof(SpecShared) / 8) + 8 * N + MPCB_SPEC_TRIALS * 6 * N;
+}
+static_assert(sizeof(SpecShared) % 16 == 0, "SpecShared keeps 16-byte granularity");
+
+template <int SPL, int FIXED>
+__device__ __forceinline__ void spec_helper(const KParams& P, SpecShared* SP, int h, int lane)
+{
+    const LayV<FIXED> LV{&P.L};
+    const int N = LV.N();
+    double* const req = reinterpret_cast<double*>(SP + 1);
+    double* const res = req + 8 * N + (size_t)h * 6 * N;
+    bool act[SPL];
+    MPCB_FORJ act[j] = lane + 32 * j < N;
+    for (;;) {
+        bar_sync(1, SPEC_THREADS);
+        if (SP->cmd == 0) return;
+        const int lsj = SP->ls0 + h;
+        if (lsj <= 10) {
+            const double tau = ldexp(1.0, -lsj);
+            const double gamma = SP->gamma;
+            double u0[SPL], u1[SPL], pt0[SPL], pt1[SPL], ya[SPL], yw[SPL];
+            MPCB_FORJ {
+                const int k = act[j] ? lane + 32 * j : 0;
+                u0[j] = act[j] ? req[k] : 0.0; u1[j] = act[j] ? req[N + k] : 0.0;
+                const double r0 = act[j] ? req[2 * N + k] : 0.0, r1 = act[j] ? req[3 * N + k] : 0.0;
+                const double d0 = act[j] ? req[4 * N + k] : 0.0, d1 = act[j] ? req[5 * N + k] : 0.0;
+                ya[j] = act[j] ? req[6 * N + k] : 0.0; yw[j] = act[j] ? req[7 * N + k] : 0.0;
+                pt0[j] = u0[j] - (1.0 - tau) * r0 - tau * d0;
+                pt1[j] = u1[j] - (1.0 - tau) * r1 - tau * d1;
+            }
+            EvalOut<SPL> o;
+            eval_psi<SPL, FIXED>(P, SP->S, pt0, pt1, SP->ceff, ya, yw, true, o, lane);
+            __syncwarp();
+            double h0[SPL], h1[SPL], s0[SPL], s1[SPL];
+            MPCB_FORJ { s0[j] = fma(-gamma, o.gv[j], pt0[j]); s1[j] = fma(-gamma, o.gw[j], pt1[j]); }
+            project_U<SPL>(P, s0, s1, h0, h1);
+            double d2 = 0.0;
+            MPCB_FORJ {
+                const double e0 = fma(-gamma, o.gv[j], pt0[j]) - h0[j], e1 = fma(-gamma, o.gw[j], pt1[j]) - h1[j];
+                d2 = fma(e0, e0, fma(e1, e1, d2));
+            }
+            d2 = warp_sum(d2);
+            const double lhs = o.psi - 0.5 * gamma * sumsq2<SPL>(o.gv, o.gw) + div_nonneg(0.5 * d2, gamma);
+            MPCB_FORJ {
+                if (act[j]) {
+                    const int k = lane + 32 * j;
+                    res[k] = pt0[j]; res[N + k] = pt1[j]; res[2 * N + k] = o.gv[j]; res[3 * N + k] = o.gw[j];
+                    res[4 * N + k] = h0[j]; res[5 * N + k] = h1[j];
+                }
+            }
+            if (lane == 0) { SP->lhs[h] = lhs; SP->cost[h] = o.psi; }
+            __syncwarp();
+            bar_sync(2, SPEC_THREADS);
+            // the next iteration opens with the cost at this trial's half step (Lipschitz check):
+            // evaluated here, ahead of need, while warp 0 updates its L-BFGS direction
+            eval_psi<SPL, FIXED>(P, SP->S, h0, h1, SP->ceff, ya, yw, false, o, lane);
+            __syncwarp();
+            if (lane == 0) SP->cost_h[h] = o.psi;
+        } else {
+            bar_sync(2, SPEC_THREADS);
+        }
+        __syncwarp();
+        bar_sync(3, SPEC_THREADS);
+    }
+}
+
 // What the pending horizon evaluation is for.  The whole ALM/PANOC run is one
 // loop around a single inlined eval_psi call site (small code footprint, no
 // solver state in local memory): every handler ends by choosing the next point
@@ -227,11 +315,12 @@ enum EvalFor { ST_INIT, ST_INIT_LIP, ST_LIP_HALF, ST_LIP_U0, ST_LIP_LOOP, ST_NOL
 //   MODE 1: queue worker — pull instances from `counter` until the batch is exhausted.
 //   TEAM: this warp is warp 0 of a team (one CTA per instance): the other warps evaluate the
 //   ellipse cost terms of every horizon evaluation (mpcb_device.cuh "team mode").
-template <int SPL, int MODE, int FIXED, bool TEAM = false>
+//   SPEC: this warp is warp 0 of a latency CTA: helper warps evaluate the line-search trials concurrently.
+template <int SPL, int MODE, int FIXED, bool TEAM = false, bool SPEC = false>
 __device__ __forceinline__ void solve_worker(const KParams& P, const double* __restrict__ S0,
                                              const double* __restrict__ staged, int* __restrict__ counter,
                                              double* lb_mem, int b0, int lane, const SolveIO& io,
-                                             TeamShared* T = nullptr)
+                                             TeamShared* T = nullptr, SpecShared* SP = nullptr)
 {
     const LayV<FIXED> LV{&P.L};
     const int N = LV.N();
@@ -259,6 +348,8 @@ __device__ __forceinline__ void solve_worker(const KParams& P, const double* __r
     int num_iter = 0, it_lip = 0, ls = 0;
     int st = ST_INIT;
     bool cont = true, flag = true, want_grad = true;
+    int spec_acc = -1;          // SPEC: helper slot whose cost at the half step is on its way
+    bool spec_dir = false;      // SPEC: the L-BFGS direction was computed ahead of the Lipschitz check
     const double EPS = 2.220446049250313e-16;
     EvalOut<SPL> o;
     CS->qscan = 0;
@@ -433,6 +524,28 @@ L_step_begin:   // ---- PANOCEngine::step
         MPCB_CS_LANE0(CS->n_small = CS->n_small + 1);
     }
     // update_lipschitz_constant: cost at the half step first
+    if constexpr (SPEC) {
+        if (spec_acc >= 0) {
+            // a helper is evaluating it; the check nearly always passes, so the L-BFGS update and
+            // two-loop recursion that follow it run now (a failed check resets the buffer anyway)
+            const int head0 = B.head;
+            const double bg0 = B.gamma;
+            lbfgs_update<SPL>(P, B, I, lane, act);
+            MPCB_FORJ { I.d0[j] = I.r0[j]; I.d1[j] = I.r1[j]; }
+            lbfgs_apply<SPL>(B, I.d0, I.d1, lane, act);
+            bar_sync(3, SPEC_THREADS);
+            cost_half = SP->cost_h[spec_acc];
+            MPCB_CS_LANE0(CS->n_cost = CS->n_cost + 1);
+            spec_acc = -1;
+            it_lip = 0;
+            want_grad = false;   // as the sequential path leaves it for the Lipschitz loop
+            const double ip = dotw<SPL>(I.g0, I.g1, I.r0, I.r1);
+            const double rhs = I.cost + 1e-6 * fabs(I.cost) - ip + ddiv(0.95, 2.0 * I.gamma) * (I.norm_r * I.norm_r);
+            if (cost_half > rhs && I.Lc < 1e9) { B.head = head0; B.gamma = bg0; }   // as if not updated
+            else spec_dir = true;
+            goto L_lip_check;
+        }
+    }
     MPCB_FORJ { pt0[j] = I.h0[j]; pt1[j] = I.h1[j]; }
     want_grad = false; st = ST_LIP_HALF;
     goto L_eval;
@@ -469,11 +582,14 @@ L_lip_check: {
     }
     I.sigma = ddiv(1.0 - 0.95, 4.0 * I.gamma);
     // lbfgs_direction
-    lbfgs_update<SPL>(P, B, I, lane, act);
-    if (I.iter > 0) {
-        MPCB_FORJ { I.d0[j] = I.r0[j]; I.d1[j] = I.r1[j]; }
-        lbfgs_apply<SPL>(B, I.d0, I.d1, lane, act);
+    if (!(SPEC && spec_dir)) {
+        lbfgs_update<SPL>(P, B, I, lane, act);
+        if (I.iter > 0) {
+            MPCB_FORJ { I.d0[j] = I.r0[j]; I.d1[j] = I.r1[j]; }
+            lbfgs_apply<SPL>(B, I.d0, I.d1, lane, act);
+        }
     }
+    spec_dir = false;
     want_grad = true;
     if (I.iter == 0) {   // update_no_linesearch
         MPCB_FORJ { I.u0[j] = I.h0[j]; I.u1[j] = I.h1[j]; pt0[j] = I.u0[j]; pt1[j] = I.u1[j]; }
@@ -491,6 +607,49 @@ L_lip_check: {
     rhs_ls = fbe - I.sigma * (I.norm_r * I.norm_r);
     tau = 1.0;
     ls = 0;
+    if constexpr (SPEC) {
+        // hand the helper warps what a trial needs, then take the first trial (in the order
+        // tau = 1, 1/2, ...) that passes, exactly as the sequential search would
+        double* const req = reinterpret_cast<double*>(SP + 1);
+        MPCB_FORJ {
+            if (act[j]) {
+                const int k = lane + 32 * j;
+                req[k] = I.u0[j]; req[N + k] = I.u1[j]; req[2 * N + k] = I.r0[j]; req[3 * N + k] = I.r1[j];
+                req[4 * N + k] = I.d0[j]; req[5 * N + k] = I.d1[j]; req[6 * N + k] = I.ya[j]; req[7 * N + k] = I.yw[j];
+            }
+        }
+        if (lane == 0) { SP->S = S; SP->gamma = I.gamma; SP->ceff = CS->c; }
+        for (;;) {
+            if (lane == 0) { SP->ls0 = ls; SP->cmd = 1; }
+            __syncwarp();
+            bar_sync(1, SPEC_THREADS);
+            bar_sync(2, SPEC_THREADS);
+            int acc = -1;
+#pragma unroll 1
+            for (int t = 0; t < MPCB_SPEC_TRIALS && acc < 0 && ls + t <= 10; ++t) {
+                MPCB_CS_LANE0(CS->n_grad = CS->n_grad + 1);
+                if (!(SP->lhs[t] > rhs_ls && ls + t < 10)) acc = t;
+            }
+            if (acc >= 0) {
+                const double* res = req + 8 * N + (size_t)acc * 6 * N;
+                I.cost = SP->cost[acc];
+                MPCB_FORJ {
+                    const int k = act[j] ? lane + 32 * j : 0;
+                    I.u0[j] = act[j] ? res[k] : 0.0; I.u1[j] = act[j] ? res[N + k] : 0.0;
+                    I.g0[j] = act[j] ? res[2 * N + k] : 0.0; I.g1[j] = act[j] ? res[3 * N + k] : 0.0;
+                    I.h0[j] = act[j] ? res[4 * N + k] : 0.0; I.h1[j] = act[j] ? res[5 * N + k] : 0.0;
+                }
+                __syncwarp();
+                spec_acc = acc;
+                break;
+            }
+            bar_sync(3, SPEC_THREADS);
+            ls += MPCB_SPEC_TRIALS;
+        }
+        I.iter++;
+        flag = true;
+        goto L_step_return;
+    }
     MPCB_FORJ {
         pt0[j] = I.u0[j] - (1.0 - tau) * I.r0[j] - tau * I.d0[j];
         pt1[j] = I.u1[j] - (1.0 - tau) * I.r1[j] - tau * I.d1[j];
@@ -538,6 +697,9 @@ L_step_return:   // PANOCOptimizer::solve: flag = step(); while (flag && cont) {
         // continue_num_iters && continue_runtime (the runtime being the iteration budget)
         cont = num_iter < P.max_inner && (P.budget <= 0 || CS->inner_total + num_iter < P.budget);
         goto L_step_begin;
+    }
+    if constexpr (SPEC) {
+        if (spec_acc >= 0) { bar_sync(3, SPEC_THREADS); spec_acc = -1; }   // unused look-ahead
     }
     {
         bool fin = true;
