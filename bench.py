@@ -485,8 +485,10 @@ def main():
                            "gpu_p50_ms_same_instances_as_cpu": float(np.percentile(wall[:ncpu], 50)),
                            "cpu_port_p50_ms": float(np.percentile(cpu_ms, 50)),
                            "cpu_port_p95_ms": float(np.percentile(cpu_ms, 95)), "cpu_solves": ncpu,
-                           "what": "wall clock of solver().run(p) incl. H2D/D2H, one instance per call (one warp on one "
-                                   "SM), reference settings, no wall-clock cap; CPU port: one thread, same instances"}
+                           "what": "wall clock of solver().run(p) incl. H2D/D2H, one instance per call (latency kernel: a "
+                                   "five-warp CTA on one SM, line-search trials evaluated concurrently, same bits as "
+                                   "the one-warp kernel), reference settings, no wall-clock cap; CPU port: one thread, "
+                                   "same instances"}
 
     # ---- the other BASELINE workloads, briefly (full lines: --workload ...)
     if args.workload == HEADLINE and not args.no_others and args.scaling == "weak":
