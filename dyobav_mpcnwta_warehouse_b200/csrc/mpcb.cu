@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(SPEC_THREADS, 2) solve_kernel_spec(const KPara
         solve_worker<SPL, 1, FIXED, false, true>(P, nullptr, staged, counter, lb, 0, lane, io, nullptr, SP);
         if (lane == 0) SP->cmd = 0;
         __syncwarp();
-        bar_sync(1, SPEC_THREADS);
+        spec_bar<1>();
     } else {
         spec_helper<SPL, FIXED>(P, SP, warp - 1, lane);
     }

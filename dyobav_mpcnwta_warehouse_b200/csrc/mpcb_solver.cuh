@@ -229,6 +229,14 @@ struct SolveIO {
 #define MPCB_SPEC_TRIALS 4
 #endif
 constexpr int SPEC_THREADS = 32 * (1 + MPCB_SPEC_TRIALS);
+// The named barriers of the latency kernel, out of line on purpose: the solving warp and the helper
+// warps meet at ONE bar.sync instruction (the same address for every thread of the CTA), which is what
+// compute-sanitizer's synccheck expects of the threads of a block.
+template <int ID>
+__device__ __noinline__ void spec_bar()
+{
+    asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(SPEC_THREADS) : "memory");
+}
 struct alignas(16) SpecShared {
     const double* S;
     double gamma, ceff;
@@ -252,7 +260,7 @@ __device__ __forceinline__ void spec_helper(const KParams& P, SpecShared* SP, in
     bool act[SPL];
     MPCB_FORJ act[j] = lane + 32 * j < N;
     for (;;) {
-        bar_sync(1, SPEC_THREADS);
+        spec_bar<1>();
         if (SP->cmd == 0) return;
         const int lsj = SP->ls0 + h;
         if (lsj <= 10) {
@@ -290,17 +298,17 @@ __device__ __forceinline__ void spec_helper(const KParams& P, SpecShared* SP, in
             }
             if (lane == 0) { SP->lhs[h] = lhs; SP->cost[h] = o.psi; }
             __syncwarp();
-            bar_sync(2, SPEC_THREADS);
+            spec_bar<2>();
             // the next iteration opens with the cost at this trial's half step (Lipschitz check):
             // evaluated here, ahead of need, while warp 0 updates its L-BFGS direction
             eval_psi<SPL, FIXED>(P, SP->S, h0, h1, SP->ceff, ya, yw, false, o, lane);
             __syncwarp();
             if (lane == 0) SP->cost_h[h] = o.psi;
         } else {
-            bar_sync(2, SPEC_THREADS);
+            spec_bar<2>();
         }
         __syncwarp();
-        bar_sync(3, SPEC_THREADS);
+        spec_bar<3>();
     }
 }
 
@@ -352,7 +360,8 @@ __device__ __forceinline__ void solve_worker(const KParams& P, const double* __r
     bool spec_dir = false;      // SPEC: the L-BFGS direction was computed ahead of the Lipschitz check
     const double EPS = 2.220446049250313e-16;
     EvalOut<SPL> o;
-    CS->qscan = 0;
+    if (lane == 0) CS->qscan = 0;
+    __syncwarp();
 
 L_fetch:
     if (MODE != 0) {
@@ -373,7 +382,7 @@ L_fetch:
                 sc = q + (t / P.starts) * nq;
                 if (P.order) sc = P.order[sc];
                 b = sc * P.starts + t % P.starts;
-                CS->qscan = qs;
+                MPCB_CS_LANE0(CS->qscan = qs);
                 break;
             }
         }
@@ -533,7 +542,7 @@ L_step_begin:   // ---- PANOCEngine::step
             lbfgs_update<SPL>(P, B, I, lane, act);
             MPCB_FORJ { I.d0[j] = I.r0[j]; I.d1[j] = I.r1[j]; }
             lbfgs_apply<SPL>(B, I.d0, I.d1, lane, act);
-            bar_sync(3, SPEC_THREADS);
+            spec_bar<3>();
             cost_half = SP->cost_h[spec_acc];
             MPCB_CS_LANE0(CS->n_cost = CS->n_cost + 1);
             spec_acc = -1;
@@ -622,8 +631,8 @@ L_lip_check: {
         for (;;) {
             if (lane == 0) { SP->ls0 = ls; SP->cmd = 1; }
             __syncwarp();
-            bar_sync(1, SPEC_THREADS);
-            bar_sync(2, SPEC_THREADS);
+            spec_bar<1>();
+            spec_bar<2>();
             int acc = -1;
 #pragma unroll 1
             for (int t = 0; t < MPCB_SPEC_TRIALS && acc < 0 && ls + t <= 10; ++t) {
@@ -643,7 +652,7 @@ L_lip_check: {
                 spec_acc = acc;
                 break;
             }
-            bar_sync(3, SPEC_THREADS);
+            spec_bar<3>();
             ls += MPCB_SPEC_TRIALS;
         }
         I.iter++;
@@ -699,7 +708,7 @@ L_step_return:   // PANOCOptimizer::solve: flag = step(); while (flag && cont) {
         goto L_step_begin;
     }
     if constexpr (SPEC) {
-        if (spec_acc >= 0) { bar_sync(3, SPEC_THREADS); spec_acc = -1; }   // unused look-ahead
+        if (spec_acc >= 0) { spec_bar<3>(); spec_acc = -1; }   // unused look-ahead
     }
     {
         bool fin = true;
