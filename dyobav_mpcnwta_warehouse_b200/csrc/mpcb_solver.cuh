@@ -232,6 +232,11 @@ constexpr int SPEC_THREADS = 32 * (1 + MPCB_SPEC_TRIALS);
 // The named barriers of the latency kernel, out of line on purpose: the solving warp and the helper
 // warps meet at ONE bar.sync instruction (the same address for every thread of the CTA), which is what
 // compute-sanitizer's synccheck expects of the threads of a block.
+#ifdef MPCB_SPEC_PROF
+#define SPEC_T(i) do { const long long t_ = clock64(); spec_t[i] += t_ - spec_t0; spec_t0 = t_; } while (0)
+#else
+#define SPEC_T(i) do { } while (0)
+#endif
 template <int ID>
 __device__ __noinline__ void spec_bar()
 {
@@ -356,6 +361,9 @@ __device__ __forceinline__ void solve_worker(const KParams& P, const double* __r
     int num_iter = 0, it_lip = 0, ls = 0;
     int st = ST_INIT;
     bool cont = true, flag = true, want_grad = true;
+#ifdef MPCB_SPEC_PROF
+    long long spec_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, spec_t0 = clock64();
+#endif
     int spec_acc = -1;          // SPEC: helper slot whose cost at the half step is on its way
     bool spec_dir = false;      // SPEC: the L-BFGS direction was computed ahead of the Lipschitz check
     const double EPS = 2.220446049250313e-16;
@@ -539,10 +547,14 @@ L_step_begin:   // ---- PANOCEngine::step
             // two-loop recursion that follow it run now (a failed check resets the buffer anyway)
             const int head0 = B.head;
             const double bg0 = B.gamma;
+            SPEC_T(2);
             lbfgs_update<SPL>(P, B, I, lane, act);
+            SPEC_T(6);
             MPCB_FORJ { I.d0[j] = I.r0[j]; I.d1[j] = I.r1[j]; }
             lbfgs_apply<SPL>(B, I.d0, I.d1, lane, act);
+            SPEC_T(3);
             spec_bar<3>();
+            SPEC_T(4);
             cost_half = SP->cost_h[spec_acc];
             MPCB_CS_LANE0(CS->n_cost = CS->n_cost + 1);
             spec_acc = -1;
@@ -631,8 +643,10 @@ L_lip_check: {
         for (;;) {
             if (lane == 0) { SP->ls0 = ls; SP->cmd = 1; }
             __syncwarp();
+            SPEC_T(0);
             spec_bar<1>();
             spec_bar<2>();
+            SPEC_T(1);
             int acc = -1;
 #pragma unroll 1
             for (int t = 0; t < MPCB_SPEC_TRIALS && acc < 0 && ls + t <= 10; ++t) {
@@ -813,6 +827,9 @@ L_finish:
             io.evals[4 * b] = CS->n_cost; io.evals[4 * b + 1] = CS->n_grad;
             io.evals[4 * b + 2] = CS->n_small; io.evals[4 * b + 3] = 0;
         }
+#ifdef MPCB_SPEC_PROF
+        if (SPEC && P.prof) for (int i = 0; i < 8; ++i) P.prof[MPCB_WS_PROF_CTAS + 8 * (b & 127) + i] = (unsigned long long)spec_t[i];
+#endif
     }
     __syncwarp();   // lane 0's output block is done before the next instance resets the counters
     if (MODE != 0) goto L_fetch;
