@@ -604,6 +604,9 @@ __global__ void __launch_bounds__(TEAM_THREADS, MPCB_TEAM_CTAS) solve_kernel_tea
     }
     __syncthreads();
     if (warp < TEAM_NS) {
+#ifdef MPCB_TEAM_REGS_SOLVER
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(MPCB_TEAM_REGS_SOLVER));
+#endif
         double* lb = base + (size_t)warp * sstride;
         TeamShared* T = reinterpret_cast<TeamShared*>(lb + P.lb_doubles);
         asm volatile("" : "+r"(lane));
@@ -611,6 +614,9 @@ __global__ void __launch_bounds__(TEAM_THREADS, MPCB_TEAM_CTAS) solve_kernel_tea
         __syncwarp();
         if (lane == 0) { __threadfence_block(); T->exit_ = 1; }
     } else {
+#ifdef MPCB_TEAM_REGS_WORKER
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(MPCB_TEAM_REGS_WORKER));
+#endif
         team_worker<FIXED>(P, base, sstride, P.lb_doubles, TEAM_NS, pool, (int)threadIdx.x - 32 * TEAM_NS);
     }
 }

@@ -225,12 +225,15 @@ constexpr int TEAM_WORKERS = TEAM_THREADS - 32 * TEAM_NS;      // worker threads
 #ifndef MPCB_TEAM_CTAS
 #define MPCB_TEAM_CTAS (12 / MPCB_TEAM_WARPS)     // resident teams per SM the register budget is cut for
 #endif
-// number of worker groups (a power of two <= 32 with G*N <= worker threads); 0: one-warp kernel
+// number of worker groups (a power of two <= 32 with G*N <= 320: part of the arithmetic contract, so a
+// constant and not the worker count of a particular build, which must be at least that); 0: one-warp kernel
+#define MPCB_TEAM_MAP_THREADS 320
+static_assert(TEAM_WORKERS >= MPCB_TEAM_MAP_THREADS, "the worker pool must cover the (step, group) mapping");
 __host__ __device__ constexpr int team_groups(int N, int Ndyn, bool force = false)
 {
     if (Ndyn < MPCB_TEAM_MIN_NDYN && !force) return 0;
     int g = 1;
-    while (2 * g <= 32 && 2 * g * N <= TEAM_WORKERS) g *= 2;
+    while (2 * g <= 32 && 2 * g * N <= MPCB_TEAM_MAP_THREADS) g *= 2;
     return g;
 }
 // Per-solver block: header, then X[N], Y[N] (request), SUM[6][N] (totals over the groups: cost, gx,
