@@ -1129,6 +1129,12 @@ __device__ __forceinline__ void team_worker(const KParams& P, double* solvers, i
     const bool CULL = P.cull != 0;
     const int NB = (N + 7) >> 3, blk = k >> 3;
     int last = NS - 1;
+#ifdef MPCB_TEAM_PROF
+    long long tp_idle = 0, tp_p1 = 0, tp_p2 = 0, tp_own = 0, tp_n = 0, tp_t = clock64();
+#define TEAM_T(acc) do { const long long t_ = clock64(); acc += t_ - tp_t; tp_t = t_; } while (0)
+#else
+#define TEAM_T(acc) do { } while (0)
+#endif
     for (;;) {
         if (t < 32) {
             // next pending request, round robin from the solver served last; -1 when every solver is
@@ -1154,7 +1160,15 @@ __device__ __forceinline__ void team_worker(const KParams& P, double* solvers, i
         }
         __syncwarp();
         bar_sync(3, TEAM_WORKERS);
+        TEAM_T(tp_idle);
         const int cur = pool->cur;
+#ifdef MPCB_TEAM_PROF
+        if (cur < 0 && (t & 31) == 0 && P.prof) {
+            unsigned long long* o = P.prof + MPCB_WS_PROF_CTAS + (size_t)(blockIdx.x & (MPCB_WS_PROF_CTAS - 1)) * MPCB_WS_PROF_WARPS;
+            o[NS + (t >> 5)] = (unsigned long long)tp_own;
+            if (t == 0) { o[12] = (unsigned long long)tp_idle; o[13] = (unsigned long long)tp_p1; o[14] = (unsigned long long)tp_p2; o[15] = (unsigned long long)tp_n; }
+        }
+#endif
         if (cur < 0) return;
         last = cur;
         TeamShared* T = reinterpret_cast<TeamShared*>(solvers + (size_t)cur * sstride + lb_doubles);
@@ -1225,33 +1239,53 @@ __device__ __forceinline__ void team_worker(const KParams& P, double* solvers, i
                     }
                 }
             }
-#pragma unroll 2
-            for (int i = g; i < Ndyn; i += G) {
+            // Two phases per chunk of 32 of the thread's ellipses: first every bounding-box test (a short
+            // loop whose loads are all in flight together: the boxes come from L2 as often as from L1),
+            // then the survivors in index order - the same terms in the same order as one fused loop.
+#pragma unroll 1
+            for (int i0 = g; i0 < Ndyn; i0 += 32 * G) {
                 // an ellipse whose bounding box misses the block's robot box is exactly zero at
                 // every step of the block (NaN boxes compare false: never skipped)
-                const float4 q0 = bx0[i], q1 = bx1[i * NB];
-                const bool in0 = !(rx0 > q0.y || rx1 < q0.x || ry0 > q0.w || ry1 < q0.z);
-                const bool in1 = !(rx0 > q1.y || rx1 < q1.x || ry0 > q1.w || ry1 < q1.z);
-                EllT a, b;
-                a.hr = 0.0; b.hr = 0.0;
-                if (in0) {                               // t = 0 slot
-                    ellipse_terms(GRAD, e0 + i, Ndyn, x, y, a);
-                    pc += a.cost;
-                    if (GRAD) { pgx += a.gx; pgy += a.gy; }
+                unsigned m0 = 0u, m1 = 0u;
+#pragma unroll 4
+                for (int j = 0; j < 32; ++j) {
+                    const int i = i0 + j * G;
+                    if (i < Ndyn) {
+                        const float4 q0 = bx0[i], q1 = bx1[i * NB];
+                        if (!(rx0 > q0.y || rx1 < q0.x || ry0 > q0.w || ry1 < q0.z)) m0 |= 1u << j;
+                        if (!(rx0 > q1.y || rx1 < q1.x || ry0 > q1.w || ry1 < q1.z)) m1 |= 1u << j;
+                    }
                 }
-                if (in1) {                               // t = k+1 slot
-                    ellipse_terms(GRAD, etb + i * N, Ndyn * N, x, y, b);
-                    pc += b.cost;
-                    if (GRAD) { pgx += b.gx; pgy += b.gy; }
+                unsigned m = m0 | m1;
+                while (m) {
+                    const int j = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int i = i0 + j * G;
+                    EllT a, b;
+                    a.hr = 0.0; b.hr = 0.0;
+                    if ((m0 >> j) & 1u) {                    // t = 0 slot
+                        ellipse_terms(GRAD, e0 + i, Ndyn, x, y, a);
+                        pc += a.cost;
+                        if (GRAD) { pgx += a.gx; pgy += a.gy; }
+                    }
+                    if ((m1 >> j) & 1u) {                    // t = k+1 slot
+                        ellipse_terms(GRAD, etb + i * N, Ndyn * N, x, y, b);
+                        pc += b.cost;
+                        if (GRAD) { pgx += b.gx; pgy += b.gy; }
+                    }
+                    if (a.hr > 0.0 || b.hr > 0.0) atomicOr(&T->hit[i >> 5], 1u << (i & 31));
                 }
-                if (a.hr > 0.0 || b.hr > 0.0) atomicOr(&T->hit[i >> 5], 1u << (i & 31));
             }
             double* q = PART + g * N + k;
             q[0] = pc; q[G * N] = pgx; q[2 * G * N] = pgy;
             q[3 * G * N] = psp; q[4 * G * N] = pspx; q[5 * G * N] = pspy;
         }
         __syncwarp();
+#ifdef MPCB_TEAM_PROF
+        tp_own += clock64() - tp_t;
+#endif
         bar_sync(3, TEAM_WORKERS);
+        TEAM_T(tp_p1);
         // ---- pass 2a: totals over the groups, in group order from +0.0 (6 quantities x N steps)
 #pragma unroll 1
         for (int idx = t; idx < 6 * N; idx += TEAM_WORKERS) {
@@ -1319,6 +1353,10 @@ __device__ __forceinline__ void team_worker(const KParams& P, double* solvers, i
         }
         __syncwarp();
         bar_sync(3, TEAM_WORKERS);
+        TEAM_T(tp_p2);
+#ifdef MPCB_TEAM_PROF
+        ++tp_n;
+#endif
         if (t == 0) {
             __threadfence_block();
             T->done = T->req;
