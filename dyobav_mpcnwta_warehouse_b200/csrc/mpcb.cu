@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(qthreads(FIXED), MPCB_MIN_CTAS) solve_kernel_q
 // the line-search trials concurrently (mpcb_solver.cuh "speculative line search").  Same bits as the
 // queue kernel.
 template <int SPL, int FIXED>
-__global__ void __launch_bounds__(SPEC_THREADS, 2) solve_kernel_spec(const KParams P, const double* __restrict__ staged,
+__global__ void __launch_bounds__(SPEC_THREADS, SPL == 1 ? SPEC_CTAS_PER_SM : 1) solve_kernel_spec(const KParams P, const double* __restrict__ staged,
                                                                      const SolveIO io, int* __restrict__ counter)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -806,10 +806,20 @@ int make_plan(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solver_cfg* c,
         P.warps = env_int("MPCB_WARPS", maxw); P.nsc = 0;
         if (P.warps < 1 || P.warps > maxw) P.warps = maxw < 8 ? maxw : 8;
         while (P.warps > 1 && 16 + P.warps * lbw > cap) --P.warps;   // large N: fewer warps per CTA
+        // a batch of fewer instances than resident warps is spread over all SMs (a warp alone on a
+        // scheduler runs an iteration 1.5x faster than beside three others) instead of filling a few
+        if (need_lbfgs && env_int("MPCB_WARPS", 0) == 0) {
+            const long long per_sm = ((long long)B + 147) / 148;
+            if (per_sm < P.warps) P.warps = per_sm < 1 ? 1 : (int)per_sm;
+        }
         pl.smem_bytes = 16 + P.warps * lbw;
     }
-    // small batches (at most two instances per SM): the latency kernel, same bits as the queue kernel
-    pl.spec = need_lbfgs && !pl.team && !pl.smem && B <= 2 * 148 && env_int("MPCB_SPEC", 1) != 0;
+    // small batches: the latency kernel, same bits as the queue kernel.  Its persistent CTAs (two per
+    // SM) pull instances from the same queues; measured against the one-warp kernel at default dims
+    // (ms per batch, 8 starts per scenario): B = 592: 160 vs 346, 1184: 194 vs 329, 1776: 274 vs 274,
+    // 2368: 313 vs 258 - a batch this small is bound by its slowest instance, which a CTA solves twice as fast
+    pl.spec = need_lbfgs && !pl.team && !pl.smem &&
+              B <= env_int("MPCB_SPEC_MAXB", (pl.spl == 1 ? 8 : 2) * 148) && env_int("MPCB_SPEC", 1) != 0;
     if (pl.spec) pl.smem_bytes = (size_t)(P.lb_doubles + spec_doubles(d->N)) * 8;
     if (pl.team) {
         // per solver warp its scratch and its team block, then the worker pool's scratch; the

@@ -217,7 +217,8 @@ struct SolveIO {
 };
 
 // ---------------------------------------------------------------- speculative line search
-// LATENCY kernel for small batches (at most two instances per SM): one CTA per instance, warp 0 runs
+// LATENCY kernel for small batches (up to eight instances per SM, two for N > 32; persistent CTAs, two
+// resident per SM, one for N > 32): one CTA per instance at a time, warp 0 runs
 // the solve as ever, SPEC_TRIALS helper warps evaluate the line-search trial points tau = 1, 1/2,
 // 1/4, ... CONCURRENTLY instead of one after the other.  PANOC's line search accepts the first trial
 // that passes the envelope test; on this problem it backtracks often (2.7 cost+gradient evaluations
@@ -226,9 +227,10 @@ struct SolveIO {
 // counters (only the trials up to the accepted one are counted) stay bit-identical to the one-warp
 // kernel and to the laned oracle.
 #ifndef MPCB_SPEC_TRIALS
-#define MPCB_SPEC_TRIALS 4
+#define MPCB_SPEC_TRIALS 6       // measured: 4 -> 6 trials per batch, p95 of a single solve 79 -> 70 ms; 8 adds nothing
 #endif
 constexpr int SPEC_THREADS = 32 * (1 + MPCB_SPEC_TRIALS);
+constexpr int SPEC_CTAS_PER_SM = SPEC_THREADS <= 224 ? 2 : 1;    // what the register budget is cut for
 // The named barriers of the latency kernel, out of line on purpose: the solving warp and the helper
 // warps meet at ONE bar.sync instruction (the same address for every thread of the CTA), which is what
 // compute-sanitizer's synccheck expects of the threads of a block.
