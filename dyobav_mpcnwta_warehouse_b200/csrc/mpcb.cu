@@ -757,6 +757,7 @@ int make_plan(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solver_cfg* c,
     P.cb_alpha = c->cbfgs_alpha;
     P.max_inner = c->max_inner; P.max_outer = c->max_outer; P.mem = c->lbfgs_mem;
     P.budget = c->max_inner_total > 0 ? c->max_inner_total : 0;
+    P.time_ns = c->max_time_us > 0 ? 1000LL * c->max_time_us : 0;
     P.n_p = n_p; P.starts = starts;
     const long long B = (long long)n_p * starts;
     if (B > 0x7fffffffLL / (2 * d->N)) return MPCB_E_DIMS;
@@ -903,7 +904,7 @@ void mpcb_default_solver_cfg(mpcb_solver_cfg* c)
     c->inner_tol_update = 0.1; c->penalty_update = 5.0; c->sufficient_decrease = 0.1;
     c->initial_penalty = 10.0; c->sy_epsilon = 1e-10; c->cbfgs_epsilon = 1e-8; c->cbfgs_alpha = 1.0;
     c->max_inner = 500; c->max_outer = 10; c->lbfgs_mem = 10; c->max_inner_total = 0;
-    c->team_mode = 0; c->reserved = 0;
+    c->team_mode = 0; c->max_time_us = 0;
 }
 
 int32_t mpcb_workspace_bytes(const mpcb_dims* d, int32_t n_p, int32_t starts, size_t* bytes)

@@ -81,6 +81,7 @@ struct KParams {
     int lb_doubles;      // per-warp L-BFGS scratch (doubles)
     int cull;            // 1: skip provably-zero obstacle terms
     int budget;          // > 0: cap on the inner iterations of one solve (cfg->max_inner_total)
+    long long time_ns;   // > 0: wall-clock cap on one solve (cfg->max_time_us; latency kernel only)
     unsigned long long* prof;   // launch profile in the workspace header (nullable): [CTAS] start, [CTAS][WARPS] finish
     const int* order;           // queue slot -> scenario, hardest first (nullable: identity)
     int team_G;                 // worker groups of the team kernels for this launch (0: one-warp kernels)

@@ -69,7 +69,9 @@ struct ColdState {
     double akkt_tol;
     double dy, dy_plus, f2n, f2n_plus, last_fpr, fcost;
     int alm_iter, n_outer, inner_total, outer, inner, status, n_cost, n_grad;
-    int failed, qscan, n_small, pad;   // sizeof == 112: keeps the scratch a whole number of double2
+    int failed, qscan, n_small, pad;
+    unsigned long long t0, pad8;       // SPEC: %globaltimer when the instance was started.  sizeof == 128: keeps
+                                       // the scratch a whole number of double2
 };
 // doubles of per-warp scratch after the L-BFGS rows: y, y+ (2N each), the parked solver vectors
 // (7 x (v, w) per horizon step), the parked PANOC scalars and the cold state
@@ -98,6 +100,13 @@ __device__ __forceinline__ void project_U(const KParams& P, const double (&a0)[S
         o0[j] = a0[j] < P.vmin ? P.vmin : (a0[j] > P.vmax ? P.vmax : a0[j]);
         o1[j] = a1[j] < -P.wmax ? -P.wmax : (a1[j] > P.wmax ? P.wmax : a1[j]);
     }
+}
+
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
 
 template <int SPL>
@@ -411,6 +420,7 @@ L_fetch:
         asm volatile("" : "+l"(S));
     }
     CS->n_cost = 0; CS->n_grad = 0; CS->n_small = 0;
+    if constexpr (SPEC) { MPCB_CS_LANE0(CS->t0 = globaltimer_ns()); }
     MPCB_FORJ {
         const int k = lane + 32 * j;
         I.u0[j] = 0.0; I.u1[j] = 0.0; I.ya[j] = 0.0; I.yw[j] = 0.0;
@@ -440,6 +450,13 @@ L_outer_begin:   // ---- AlmOptimizer::step: project y on Y, then the inner prob
     // AlmOptimizer::solve checks the remaining time before every outer iteration; here the clock
     // is the inner-iteration count (cfg->max_inner_total, 0 = off)
     if (P.budget > 0 && CS->inner_total >= P.budget) { CS->status = MPCB_NOT_CONVERGED_OUT_OF_TIME; goto L_finish; }
+    if constexpr (SPEC) {
+        // ... and, in the latency kernel, the reference's own rule: the wall clock (cfg->max_time_us)
+        if (P.time_ns > 0) {
+            const bool late = (long long)(__shfl_sync(FULL, globaltimer_ns(), 0) - CS->t0) >= P.time_ns;
+            if (late) { CS->status = MPCB_NOT_CONVERGED_OUT_OF_TIME; goto L_finish; }
+        }
+    }
     MPCB_CS_LANE0(CS->n_outer = CS->n_outer + 1);
     MPCB_FORJ {
         const int k = lane + 32 * j;
@@ -721,6 +738,9 @@ L_step_return:   // PANOCOptimizer::solve: flag = step(); while (flag && cont) {
         ++num_iter;
         // continue_num_iters && continue_runtime (the runtime being the iteration budget)
         cont = num_iter < P.max_inner && (P.budget <= 0 || CS->inner_total + num_iter < P.budget);
+        if constexpr (SPEC) {
+            if (P.time_ns > 0) cont = cont && (long long)(__shfl_sync(FULL, globaltimer_ns(), 0) - CS->t0) < P.time_ns;
+        }
         goto L_step_begin;
     }
     if constexpr (SPEC) {

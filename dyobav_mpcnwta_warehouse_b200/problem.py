@@ -51,7 +51,7 @@ class CSolverCfg(ctypes.Structure):
         "cbfgs_epsilon", "cbfgs_alpha")] + [
         ("max_inner", ctypes.c_int32), ("max_outer", ctypes.c_int32),
         ("lbfgs_mem", ctypes.c_int32), ("max_inner_total", ctypes.c_int32),
-        ("team_mode", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+        ("team_mode", ctypes.c_int32), ("max_time_us", ctypes.c_int32)]
 
 
 @dataclass(frozen=True)
@@ -148,6 +148,10 @@ class SolverSettings:
     # by the laned oracle.  Meant as a latency mode for single solves; measured on B200 it only pays when
     # the per-step part of an evaluation is large (for the reference's dims it is 1.4x SLOWER).
     team_mode: int = 0
+    # 0 = off.  Wall-clock cap on one solve in microseconds: the reference's ``max_solver_time``
+    # (mpc_builder.py:189) itself.  Honoured for small batches (the latency kernel: the single solve per
+    # timestep); exhausted -> "NotConvergedOutOfTime".  Results then depend on timing, as the reference's do.
+    max_time_us: int = 0
 
     def __post_init__(self):
         if not (1 <= self.lbfgs_mem <= MAX_LBFGS):
@@ -158,7 +162,8 @@ class SolverSettings:
                           self.inner_tol_update, self.penalty_update,
                           self.sufficient_decrease, self.initial_penalty, self.sy_epsilon,
                           self.cbfgs_epsilon, self.cbfgs_alpha, self.max_inner,
-                          self.max_outer, self.lbfgs_mem, int(self.max_inner_total), int(self.team_mode), 0)
+                          self.max_outer, self.lbfgs_mem, int(self.max_inner_total), int(self.team_mode),
+                          int(self.max_time_us))
 
 
 # The yaml keys of config/mpc_fast.yaml / mpc_default.yaml with their shipped

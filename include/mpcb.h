@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MPCB_ABI_VERSION 3
+#define MPCB_ABI_VERSION 4
 
 /* ---- error codes --------------------------------------------------------- */
 #define MPCB_OK            0
@@ -41,7 +41,7 @@ extern "C" {
  *      config/mpc_fast.yaml:48 `bad_exit_codes` refers to) ------------------- */
 #define MPCB_CONVERGED                   0
 #define MPCB_NOT_CONVERGED_ITERATIONS    1
-#define MPCB_NOT_CONVERGED_OUT_OF_TIME   2  /* only with cfg->max_inner_total > 0 (iteration budget) */
+#define MPCB_NOT_CONVERGED_OUT_OF_TIME   2  /* only with cfg->max_inner_total > 0 (iteration budget) or cfg->max_time_us > 0 */
 #define MPCB_NOT_FINITE_COMPUTATION      3
 
 /*
@@ -104,7 +104,15 @@ typedef struct mpcb_solver_cfg {
                                   * team_mode 0 by round-off.  Meant as a latency mode for single solves;
                                   * measured on B200 it pays only when the per-step part of an evaluation
                                   * is large (reference dims: 28.7 vs 20.8 us per inner iteration).     */
-    int32_t reserved;
+    int32_t max_time_us;         /* 0 = off.  Wall-clock cap on ONE solve in microseconds, the reference's
+                                  * max_solver_time itself (with_max_duration_micros, mpc_builder.py:189;
+                                  * 100 000 in mpc_fast.yaml:45): the time since the instance was started is
+                                  * checked before every outer iteration and after every inner iteration, as
+                                  * AlmOptimizer::solve / PANOCOptimizer::solve do; exhausted ->
+                                  * MPCB_NOT_CONVERGED_OUT_OF_TIME.  Results then depend on timing (as the
+                                  * reference's do).  Honoured by the latency kernel, i.e. for batches of up to
+                                  * eight instances per SM and dims without team kernels - the single solve per
+                                  * timestep; larger batches ignore it (max_inner_total is their budget).   */
 } mpcb_solver_cfg;
 
 #define MPCB_MAX_LBFGS 10

@@ -18,7 +18,7 @@ def test_header_symbols_all_exported(cuda_solver_lib):
     assert declared == set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(cuda_solver_lib, name), name
-    assert cuda_solver_lib.mpcb_abi_version() == 3
+    assert cuda_solver_lib.mpcb_abi_version() == 4
 
 
 def test_param_len_matches_reference_layout(cuda_solver_lib):

@@ -90,6 +90,8 @@ def test_generated_dropin_module(tmp_path, monkeypatch):
     built = importlib.import_module("navi_fast")
     s = built.solver()
     assert hasattr(s, "run") and s.dims == Dims()
+    # the yaml's wall-clock cap (max_solver_time, microseconds: mpc_builder.py:189) travels into the module
+    assert s.settings.max_time_us == 100_000 and s.settings.max_inner_total == 0
     with pytest.raises(RuntimeError, match="3003"):
         s.run([0.0] * 5)
     import torch
