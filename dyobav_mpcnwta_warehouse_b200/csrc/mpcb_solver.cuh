@@ -609,9 +609,13 @@ H_LIP_LOOP:
     goto L_lip_check;
 
 L_lip_check: {
-    const double ip = dotw<SPL>(I.g0, I.g1, I.r0, I.r1);
-    const double rhs = I.cost + 1e-6 * fabs(I.cost) - ip + ddiv(0.95, 2.0 * I.gamma) * (I.norm_r * I.norm_r);
-    if (cost_half > rhs && it_lip < 10 && I.Lc < 1e9) {
+    bool lip_fail = false;
+    if (!(SPEC && spec_dir)) {   // (the latency kernel's look-ahead path has made this very test already: passed)
+        const double ip = dotw<SPL>(I.g0, I.g1, I.r0, I.r1);
+        const double rhs = I.cost + 1e-6 * fabs(I.cost) - ip + ddiv(0.95, 2.0 * I.gamma) * (I.norm_r * I.norm_r);
+        lip_fail = cost_half > rhs && it_lip < 10 && I.Lc < 1e9;
+    }
+    if (lip_fail) {
         B.reset();
         I.Lc *= 2.0;
         I.gamma /= 2.0;
