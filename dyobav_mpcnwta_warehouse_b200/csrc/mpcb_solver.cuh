@@ -212,6 +212,54 @@ __device__ __forceinline__ void lbfgs_apply(Lbfgs<SPL>& B, double (&q0)[SPL], do
     }
 }
 
+// The same recursion with the rows of the next step loaded before the reduction of the current one (the
+// latency kernel's lone solving warp has nothing else to cover the shared-memory latency with).  Same
+// operations in the same order: same bits.
+template <int SPL>
+__device__ __forceinline__ void lbfgs_apply_prefetch(Lbfgs<SPL>& B, double (&q0)[SPL], double (&q1)[SPL],
+                                                     int lane, const bool (&act)[SPL])
+{
+    if (B.active == 0) return;
+    double sv0[SPL], sv1[SPL], yv0[SPL], yv1[SPL], rho;
+    auto load = [&](int k) {
+        const int row = B.phys(k);
+        const double* sr = B.s + row * 2 * B.N;
+        const double* yr = B.y + row * 2 * B.N;
+        MPCB_FORJ {
+            const int kk = act[j] ? lane + 32 * j : 0;
+            sv0[j] = act[j] ? sr[kk] : 0.0; sv1[j] = act[j] ? sr[B.N + kk] : 0.0;
+            yv0[j] = act[j] ? yr[kk] : 0.0; yv1[j] = act[j] ? yr[B.N + kk] : 0.0;
+        }
+        rho = B.rho[row];
+    };
+    load(0);
+#pragma unroll 1
+    for (int k = 0; k < B.active; ++k) {
+        const int row = B.phys(k);
+        double part = 0.0, c0[SPL], c1[SPL];
+        MPCB_FORJ { part = fma(sv0[j], q0[j], fma(sv1[j], q1[j], part)); c0[j] = yv0[j]; c1[j] = yv1[j]; }
+        const double rk = rho;
+        if (k + 1 < B.active) load(k + 1);
+        const double a = rk * warp_sum(part);
+        if (lane == 0) B.alpha[row] = a;
+        MPCB_FORJ { q0[j] = fma(-a, c0[j], q0[j]); q1[j] = fma(-a, c1[j], q1[j]); }
+    }
+    __syncwarp();
+    MPCB_FORJ { q0[j] *= B.gamma; q1[j] *= B.gamma; }
+    load(B.active - 1);
+#pragma unroll 1
+    for (int k = B.active - 1; k >= 0; --k) {
+        const int row = B.phys(k);
+        double part = 0.0, c0[SPL], c1[SPL];
+        MPCB_FORJ { part = fma(yv0[j], q0[j], fma(yv1[j], q1[j], part)); c0[j] = sv0[j]; c1[j] = sv1[j]; }
+        const double rk = rho, al = B.alpha[row];
+        if (k > 0) load(k - 1);
+        const double beta = rk * warp_sum(part);
+        const double cf = al - beta;
+        MPCB_FORJ { q0[j] = fma(cf, c0[j], q0[j]); q1[j] = fma(cf, c1[j], q1[j]); }
+    }
+}
+
 template <int SPL>
 __device__ __forceinline__ void compute_fpr(Inst<SPL>& I)
 {
@@ -375,6 +423,8 @@ __device__ __forceinline__ void solve_worker(const KParams& P, const double* __r
 #ifdef MPCB_SPEC_PROF
     long long spec_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, spec_t0 = clock64();
 #endif
+    double spec_fbe = 0.0;      // SPEC: the envelope value of the accepted trial (= the next iteration's FBE
+    bool spec_fbe_ok = false;   //       as long as gamma has not changed since)
     int spec_acc = -1;          // SPEC: helper slot whose cost at the half step is on its way
     bool spec_dir = false;      // SPEC: the L-BFGS direction was computed ahead of the Lipschitz check
     const double EPS = 2.220446049250313e-16;
@@ -471,6 +521,7 @@ L_outer_begin:   // ---- AlmOptimizer::step: project y on Y, then the inner prob
         I.yw[j] = yw_ / fmax(CS->c, 1.0);
     }
     // PANOCEngine::init
+    spec_fbe_ok = false;
     B.reset();
     I.iter = 0; num_iter = 0; cont = true;
     MPCB_FORJ { pt0[j] = I.u0[j]; pt1[j] = I.u1[j]; }
@@ -570,7 +621,7 @@ L_step_begin:   // ---- PANOCEngine::step
             lbfgs_update<SPL>(P, B, I, lane, act);
             SPEC_T(6);
             MPCB_FORJ { I.d0[j] = I.r0[j]; I.d1[j] = I.r1[j]; }
-            lbfgs_apply<SPL>(B, I.d0, I.d1, lane, act);
+            lbfgs_apply_prefetch<SPL>(B, I.d0, I.d1, lane, act);
             SPEC_T(3);
             spec_bar<3>();
             SPEC_T(4);
@@ -616,6 +667,7 @@ L_lip_check: {
         lip_fail = cost_half > rhs && it_lip < 10 && I.Lc < 1e9;
     }
     if (lip_fail) {
+        spec_fbe_ok = false;
         B.reset();
         I.Lc *= 2.0;
         I.gamma /= 2.0;
@@ -641,13 +693,20 @@ L_lip_check: {
         goto L_eval;
     }
     // linesearch on the forward-backward envelope
-    double dd = 0.0;
-    MPCB_FORJ {   // gradient step of the current iterate: the operands it was last computed from
-        const double e0 = fma(-I.gamma, I.g0[j], I.u0[j]) - I.h0[j], e1 = fma(-I.gamma, I.g1[j], I.u1[j]) - I.h1[j];
-        dd = fma(e0, e0, fma(e1, e1, dd));
+    double fbe;
+    if (SPEC && spec_fbe_ok) {
+        // the helper that evaluated the accepted trial computed exactly this expression from exactly
+        // these operands (its envelope test): taken over instead of two more reductions
+        fbe = spec_fbe;
+    } else {
+        double dd = 0.0;
+        MPCB_FORJ {   // gradient step of the current iterate: the operands it was last computed from
+            const double e0 = fma(-I.gamma, I.g0[j], I.u0[j]) - I.h0[j], e1 = fma(-I.gamma, I.g1[j], I.u1[j]) - I.h1[j];
+            dd = fma(e0, e0, fma(e1, e1, dd));
+        }
+        const double dist2 = warp_sum(dd);
+        fbe = I.cost - 0.5 * I.gamma * sumsq2<SPL>(I.g0, I.g1) + div_nonneg(0.5 * dist2, I.gamma);
     }
-    const double dist2 = warp_sum(dd);
-    const double fbe = I.cost - 0.5 * I.gamma * sumsq2<SPL>(I.g0, I.g1) + div_nonneg(0.5 * dist2, I.gamma);
     rhs_ls = fbe - I.sigma * (I.norm_r * I.norm_r);
     tau = 1.0;
     ls = 0;
@@ -687,6 +746,8 @@ L_lip_check: {
                 }
                 __syncwarp();
                 spec_acc = acc;
+                spec_fbe = SP->lhs[acc];
+                spec_fbe_ok = true;
                 break;
             }
             spec_bar<3>();
