@@ -572,11 +572,14 @@ __global__ void __launch_bounds__(SPEC_THREADS, SPL == 1 ? SPEC_CTAS_PER_SM : 1)
     if (warp == 0) {
         asm volatile("" : "+r"(lane));
         solve_worker<SPL, 1, FIXED, false, true>(P, nullptr, staged, counter, lb, 0, lane, io, nullptr, SP);
-        if (lane == 0) SP->cmd = 0;
+        if (lane == 0) { SP->cmd = 0; SP->la_cmd = 0; }
         __syncwarp();
         spec_bar<1>();
-    } else {
+        spec_bar<3>();
+    } else if (warp <= MPCB_SPEC_TRIALS) {
         spec_helper<SPL, FIXED>(P, SP, warp - 1, lane);
+    } else {
+        spec_lookahead<SPL, FIXED>(P, SP, lane);
     }
 }
 

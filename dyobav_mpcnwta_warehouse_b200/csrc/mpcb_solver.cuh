@@ -286,8 +286,10 @@ struct SolveIO {
 #ifndef MPCB_SPEC_TRIALS
 #define MPCB_SPEC_TRIALS 6       // measured: 4 -> 6 trials per batch, p95 of a single solve 79 -> 70 ms; 8 adds nothing
 #endif
-constexpr int SPEC_THREADS = 32 * (1 + MPCB_SPEC_TRIALS);
-constexpr int SPEC_CTAS_PER_SM = SPEC_THREADS <= 224 ? 2 : 1;    // what the register budget is cut for
+// warp 0 solves, warps 1..TRIALS evaluate line-search trials, the last warp evaluates the look-ahead cost
+constexpr int SPEC_THREADS = 32 * (2 + MPCB_SPEC_TRIALS);
+constexpr int SPEC_TRIAL_THREADS = 32 * (1 + MPCB_SPEC_TRIALS);   // barriers 1, 2: solver + trial warps
+constexpr int SPEC_CTAS_PER_SM = SPEC_THREADS <= 256 ? 2 : 1;     // what the register budget is cut for
 // The named barriers of the latency kernel, out of line on purpose: the solving warp and the helper
 // warps meet at ONE bar.sync instruction (the same address for every thread of the CTA), which is what
 // compute-sanitizer's synccheck expects of the threads of a block.
@@ -296,21 +298,28 @@ constexpr int SPEC_CTAS_PER_SM = SPEC_THREADS <= 224 ? 2 : 1;    // what the reg
 #else
 #define SPEC_T(i) do { } while (0)
 #endif
+// Barriers 1 / 2: a trial batch is published / evaluated (solver + trial warps); 3 / 4: a look-ahead
+// request is published / served (solver + look-ahead warp).
 template <int ID>
 __device__ __noinline__ void spec_bar()
 {
-    asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(SPEC_THREADS) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(ID <= 2 ? SPEC_TRIAL_THREADS : 64) : "memory");
 }
 struct alignas(16) SpecShared {
     const double* S;
     double gamma, ceff;
-    int cmd, ls0, pad0, pad1;
-    double lhs[MPCB_SPEC_TRIALS], cost[MPCB_SPEC_TRIALS], cost_h[MPCB_SPEC_TRIALS];
+    int cmd, ls0, par, la_cmd;     // par: which of the two result buffers the current batch fills
+    int la_acc, la_par, pad0, pad1;   // look-ahead request: the half step of result (la_par, la_acc)
+    double la_cost;                // ... and its answer
+    double pad2;
+    double lhs[MPCB_SPEC_TRIALS], cost[MPCB_SPEC_TRIALS];
 };
-// doubles: header, request vectors [8][N] (u0,u1,r0,r1,d0,d1,ya,yw), results [TRIALS][6][N] (pt0,pt1,g0,g1,h0,h1)
+// doubles: header, request vectors [8][N] (u0,u1,r0,r1,d0,d1,ya,yw), results [2][TRIALS][6][N]
+// (pt0,pt1,g0,g1,h0,h1; two buffers: the look-ahead warp reads the accepted half step of one batch while
+// the next batch is being written)
 __host__ __device__ constexpr int spec_doubles(int N)
 {
-    return (int)(sizeof(SpecShared) / 8) + 8 * N + MPCB_SPEC_TRIALS * 6 * N;
+    return (int)(sizeof(SpecShared) / 8) + 8 * N + 2 * MPCB_SPEC_TRIALS * 6 * N;
 }
 static_assert(sizeof(SpecShared) % 16 == 0, "SpecShared keeps 16-byte granularity");
 
@@ -320,12 +329,12 @@ __device__ __forceinline__ void spec_helper(const KParams& P, SpecShared* SP, in
     const LayV<FIXED> LV{&P.L};
     const int N = LV.N();
     double* const req = reinterpret_cast<double*>(SP + 1);
-    double* const res = req + 8 * N + (size_t)h * 6 * N;
     bool act[SPL];
     MPCB_FORJ act[j] = lane + 32 * j < N;
     for (;;) {
         spec_bar<1>();
         if (SP->cmd == 0) return;
+        double* const res = req + 8 * N + (size_t)(SP->par * MPCB_SPEC_TRIALS + h) * 6 * N;
         const int lsj = SP->ls0 + h;
         if (lsj <= 10) {
             const double tau = ldexp(1.0, -lsj);
@@ -361,18 +370,41 @@ __device__ __forceinline__ void spec_helper(const KParams& P, SpecShared* SP, in
                 }
             }
             if (lane == 0) { SP->lhs[h] = lhs; SP->cost[h] = o.psi; }
-            __syncwarp();
-            spec_bar<2>();
-            // the next iteration opens with the cost at this trial's half step (Lipschitz check):
-            // evaluated here, ahead of need, while warp 0 updates its L-BFGS direction
-            eval_psi<SPL, FIXED>(P, SP->S, h0, h1, SP->ceff, ya, yw, false, o, lane);
-            __syncwarp();
-            if (lane == 0) SP->cost_h[h] = o.psi;
-        } else {
-            spec_bar<2>();
         }
         __syncwarp();
+        spec_bar<2>();
+    }
+}
+
+// The look-ahead warp of the latency kernel: the next iteration opens with the cost at the accepted
+// trial's half step (Lipschitz test); it is evaluated here while the solving warp updates its L-BFGS
+// direction AND while the next trial batch runs - the test nearly always passes and nothing after it
+// depends on that cost, so the solving warp looks at the answer one batch later (and, when the test
+// fails after all, throws that batch away and takes the sequential path from the test on).
+template <int SPL, int FIXED>
+__device__ __forceinline__ void spec_lookahead(const KParams& P, SpecShared* SP, int lane)
+{
+    const LayV<FIXED> LV{&P.L};
+    const int N = LV.N();
+    const double* const req = reinterpret_cast<const double*>(SP + 1);
+    bool act[SPL];
+    MPCB_FORJ act[j] = lane + 32 * j < N;
+    for (;;) {
         spec_bar<3>();
+        if (SP->la_cmd == 0) return;
+        const double* res = req + 8 * N + (size_t)(SP->la_par * MPCB_SPEC_TRIALS + SP->la_acc) * 6 * N;
+        double h0[SPL], h1[SPL], ya[SPL], yw[SPL];
+        MPCB_FORJ {
+            const int k = act[j] ? lane + 32 * j : 0;
+            h0[j] = act[j] ? res[4 * N + k] : 0.0; h1[j] = act[j] ? res[5 * N + k] : 0.0;
+            ya[j] = act[j] ? req[6 * N + k] : 0.0; yw[j] = act[j] ? req[7 * N + k] : 0.0;
+        }
+        EvalOut<SPL> o;
+        eval_psi<SPL, FIXED>(P, SP->S, h0, h1, SP->ceff, ya, yw, false, o, lane);
+        __syncwarp();
+        if (lane == 0) SP->la_cost = o.psi;
+        __syncwarp();
+        spec_bar<4>();
     }
 }
 
@@ -425,7 +457,10 @@ __device__ __forceinline__ void solve_worker(const KParams& P, const double* __r
 #endif
     double spec_fbe = 0.0;      // SPEC: the envelope value of the accepted trial (= the next iteration's FBE
     bool spec_fbe_ok = false;   //       as long as gamma has not changed since)
-    int spec_acc = -1;          // SPEC: helper slot whose cost at the half step is on its way
+    bool la_pending = false;    // SPEC: the cost at the half step is on its way (look-ahead warp)
+    int spec_head0 = 0;         // SPEC: L-BFGS ring head and scaling before the update made ahead of the
+    double spec_bg0 = 1.0;      //       Lipschitz test (restored if the test fails after all)
+    int spec_par = 0;           // SPEC: result buffer of the current trial batch
     bool spec_dir = false;      // SPEC: the L-BFGS direction was computed ahead of the Lipschitz check
     const double EPS = 2.220446049250313e-16;
     EvalOut<SPL> o;
@@ -612,28 +647,20 @@ L_step_begin:   // ---- PANOCEngine::step
     }
     // update_lipschitz_constant: cost at the half step first
     if constexpr (SPEC) {
-        if (spec_acc >= 0) {
-            // a helper is evaluating it; the check nearly always passes, so the L-BFGS update and
-            // two-loop recursion that follow it run now (a failed check resets the buffer anyway)
-            const int head0 = B.head;
-            const double bg0 = B.gamma;
+        if (la_pending) {
+            // the look-ahead warp is evaluating it; the test nearly always passes and nothing after it
+            // depends on that cost, so the L-BFGS update, the two-loop recursion and the next trial batch
+            // go ahead now and the test is made when that batch comes back (H_LS part of this block)
+            spec_head0 = B.head;
+            spec_bg0 = B.gamma;
             SPEC_T(2);
             lbfgs_update<SPL>(P, B, I, lane, act);
             SPEC_T(6);
             MPCB_FORJ { I.d0[j] = I.r0[j]; I.d1[j] = I.r1[j]; }
             lbfgs_apply_prefetch<SPL>(B, I.d0, I.d1, lane, act);
             SPEC_T(3);
-            spec_bar<3>();
-            SPEC_T(4);
-            cost_half = SP->cost_h[spec_acc];
-            MPCB_CS_LANE0(CS->n_cost = CS->n_cost + 1);
-            spec_acc = -1;
             it_lip = 0;
-            want_grad = false;   // as the sequential path leaves it for the Lipschitz loop
-            const double ip = dotw<SPL>(I.g0, I.g1, I.r0, I.r1);
-            const double rhs = I.cost + 1e-6 * fabs(I.cost) - ip + ddiv(0.95, 2.0 * I.gamma) * (I.norm_r * I.norm_r);
-            if (cost_half > rhs && I.Lc < 1e9) { B.head = head0; B.gamma = bg0; }   // as if not updated
-            else spec_dir = true;
+            spec_dir = true;
             goto L_lip_check;
         }
     }
@@ -723,12 +750,33 @@ L_lip_check: {
         }
         if (lane == 0) { SP->S = S; SP->gamma = I.gamma; SP->ceff = CS->c; }
         for (;;) {
-            if (lane == 0) { SP->ls0 = ls; SP->cmd = 1; }
+            spec_par ^= 1;
+            if (lane == 0) { SP->ls0 = ls; SP->par = spec_par; SP->cmd = 1; }
             __syncwarp();
             SPEC_T(0);
             spec_bar<1>();
             spec_bar<2>();
             SPEC_T(1);
+            if (la_pending) {
+                // the Lipschitz test this step went past: cost at the half step from the look-ahead warp
+                spec_bar<4>();
+                SPEC_T(4);
+                la_pending = false;
+                cost_half = SP->la_cost;
+                MPCB_CS_LANE0(CS->n_cost = CS->n_cost + 1);
+                const double ip = dotw<SPL>(I.g0, I.g1, I.r0, I.r1);
+                const double rhs = I.cost + 1e-6 * fabs(I.cost) - ip + ddiv(0.95, 2.0 * I.gamma) * (I.norm_r * I.norm_r);
+                if (cost_half > rhs && I.Lc < 1e9) {
+                    // it fails after all: the batch just evaluated is not part of the sequential run (not
+                    // counted, not used); the L-BFGS buffer is reset by the failing branch, ring head and
+                    // scaling are put back, and the step goes on from the test as the one-warp kernel would
+                    B.head = spec_head0; B.gamma = spec_bg0;
+                    it_lip = 0;
+                    want_grad = false;
+                    spec_dir = false;
+                    goto L_lip_check;
+                }
+            }
             int acc = -1;
 #pragma unroll 1
             for (int t = 0; t < MPCB_SPEC_TRIALS && acc < 0 && ls + t <= 10; ++t) {
@@ -736,7 +784,7 @@ L_lip_check: {
                 if (!(SP->lhs[t] > rhs_ls && ls + t < 10)) acc = t;
             }
             if (acc >= 0) {
-                const double* res = req + 8 * N + (size_t)acc * 6 * N;
+                const double* res = req + 8 * N + (size_t)(spec_par * MPCB_SPEC_TRIALS + acc) * 6 * N;
                 I.cost = SP->cost[acc];
                 MPCB_FORJ {
                     const int k = act[j] ? lane + 32 * j : 0;
@@ -744,13 +792,16 @@ L_lip_check: {
                     I.g0[j] = act[j] ? res[2 * N + k] : 0.0; I.g1[j] = act[j] ? res[3 * N + k] : 0.0;
                     I.h0[j] = act[j] ? res[4 * N + k] : 0.0; I.h1[j] = act[j] ? res[5 * N + k] : 0.0;
                 }
-                __syncwarp();
-                spec_acc = acc;
                 spec_fbe = SP->lhs[acc];
                 spec_fbe_ok = true;
+                // hand the accepted half step to the look-ahead warp
+                __syncwarp();
+                if (lane == 0) { SP->la_acc = acc; SP->la_par = spec_par; SP->la_cmd = 1; }
+                __syncwarp();
+                spec_bar<3>();
+                la_pending = true;
                 break;
             }
-            spec_bar<3>();
             ls += MPCB_SPEC_TRIALS;
         }
         I.iter++;
@@ -809,7 +860,7 @@ L_step_return:   // PANOCOptimizer::solve: flag = step(); while (flag && cont) {
         goto L_step_begin;
     }
     if constexpr (SPEC) {
-        if (spec_acc >= 0) { spec_bar<3>(); spec_acc = -1; }   // unused look-ahead
+        if (la_pending) { spec_bar<4>(); la_pending = false; }   // unused look-ahead
     }
     {
         bool fin = true;
