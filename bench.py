@@ -496,7 +496,7 @@ def main():
         for name in ("warehouse_b4096_ndyn40", "dense_crowd_n40"):
             w2 = instances.workload(name)
             # warm-up batch: larger than the latency kernel's range, so that it runs the kernel that is timed
-            warm = 296 if name == "dense_crowd_n40" else 1332
+            warm = 296 if name == "dense_crowd_n40" else 1924
             r2 = measure(w2, PER_GPU_SCENARIOS[name] * world, 1, 3, full=False, warm_scenarios=warm)
             if rank == 0:
                 rf = roofline_of(r2, fp64_peak, fp64_nominal, peak_src, name)

@@ -820,10 +820,11 @@ int make_plan(const mpcb_dims* d, const mpcb_robot* r, const mpcb_solver_cfg* c,
     }
     // small batches: the latency kernel, same bits as the queue kernel.  Its persistent CTAs (two per
     // SM) pull instances from the same queues; measured against the one-warp kernel at default dims
-    // (ms per batch, 8 starts per scenario): B = 592: 160 vs 346, 1184: 194 vs 329, 1776: 274 vs 274,
-    // 2368: 313 vs 258 - a batch this small is bound by its slowest instance, which a CTA solves twice as fast
+    // (ms per batch, 8 starts per scenario): B = 592: 115 vs 346, 1184: 168 vs 329, 1776: 245 vs 266,
+    // 2072: 246 vs 246, 2368: 273 vs 257 - a batch this small is bound by its slowest instance, which a CTA
+    // solves twice as fast
     pl.spec = need_lbfgs && !pl.team && !pl.smem &&
-              B <= env_int("MPCB_SPEC_MAXB", (pl.spl == 1 ? 8 : 2) * 148) && env_int("MPCB_SPEC", 1) != 0;
+              B <= env_int("MPCB_SPEC_MAXB", (pl.spl == 1 ? 12 : 2) * 148) && env_int("MPCB_SPEC", 1) != 0;
     if (pl.spec) pl.smem_bytes = (size_t)(P.lb_doubles + spec_doubles(d->N)) * 8;
     if (pl.team) {
         // per solver warp its scratch and its team block, then the worker pool's scratch; the

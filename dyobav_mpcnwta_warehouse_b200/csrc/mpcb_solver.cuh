@@ -274,7 +274,7 @@ struct SolveIO {
 };
 
 // ---------------------------------------------------------------- speculative line search
-// LATENCY kernel for small batches (up to eight instances per SM, two for N > 32; persistent CTAs, two
+// LATENCY kernel for small batches (up to twelve instances per SM, two for N > 32; persistent CTAs, two
 // resident per SM, one for N > 32): one CTA per instance at a time, warp 0 runs
 // the solve as ever, SPEC_TRIALS helper warps evaluate the line-search trial points tau = 1, 1/2,
 // 1/4, ... CONCURRENTLY instead of one after the other.  PANOC's line search accepts the first trial
@@ -311,6 +311,8 @@ struct alignas(16) SpecShared {
     int cmd, ls0, par, la_cmd;     // par: which of the two result buffers the current batch fills
     int la_acc, la_par, pad0, pad1;   // look-ahead request: the half step of result (la_par, la_acc)
     double la_cost;                // ... and its answer
+    double la_ceff;                // the look-ahead warp's own copy of what is constant over an inner problem
+    const double* la_S;            // (written while that warp is idle: the first line search of the problem)
     double pad2;
     double lhs[MPCB_SPEC_TRIALS], cost[MPCB_SPEC_TRIALS];
 };
@@ -319,7 +321,7 @@ struct alignas(16) SpecShared {
 // the next batch is being written)
 __host__ __device__ constexpr int spec_doubles(int N)
 {
-    return (int)(sizeof(SpecShared) / 8) + 8 * N + 2 * MPCB_SPEC_TRIALS * 6 * N;
+    return (int)(sizeof(SpecShared) / 8) + 8 * N + 2 * MPCB_SPEC_TRIALS * 6 * N + 2 * N;   // + ya, yw of the look-ahead warp
 }
 static_assert(sizeof(SpecShared) % 16 == 0, "SpecShared keeps 16-byte granularity");
 
@@ -393,14 +395,15 @@ __device__ __forceinline__ void spec_lookahead(const KParams& P, SpecShared* SP,
         spec_bar<3>();
         if (SP->la_cmd == 0) return;
         const double* res = req + 8 * N + (size_t)(SP->la_par * MPCB_SPEC_TRIALS + SP->la_acc) * 6 * N;
+        const double* lay = req + 8 * N + (size_t)2 * MPCB_SPEC_TRIALS * 6 * N;
         double h0[SPL], h1[SPL], ya[SPL], yw[SPL];
         MPCB_FORJ {
             const int k = act[j] ? lane + 32 * j : 0;
             h0[j] = act[j] ? res[4 * N + k] : 0.0; h1[j] = act[j] ? res[5 * N + k] : 0.0;
-            ya[j] = act[j] ? req[6 * N + k] : 0.0; yw[j] = act[j] ? req[7 * N + k] : 0.0;
+            ya[j] = act[j] ? lay[k] : 0.0; yw[j] = act[j] ? lay[N + k] : 0.0;
         }
         EvalOut<SPL> o;
-        eval_psi<SPL, FIXED>(P, SP->S, h0, h1, SP->ceff, ya, yw, false, o, lane);
+        eval_psi<SPL, FIXED>(P, SP->la_S, h0, h1, SP->la_ceff, ya, yw, false, o, lane);
         __syncwarp();
         if (lane == 0) SP->la_cost = o.psi;
         __syncwarp();
@@ -457,6 +460,7 @@ __device__ __forceinline__ void solve_worker(const KParams& P, const double* __r
 #endif
     double spec_fbe = 0.0;      // SPEC: the envelope value of the accepted trial (= the next iteration's FBE
     bool spec_fbe_ok = false;   //       as long as gamma has not changed since)
+    bool spec_la_in = false;    // SPEC: the look-ahead warp holds this inner problem's multipliers and penalty
     bool la_pending = false;    // SPEC: the cost at the half step is on its way (look-ahead warp)
     int spec_head0 = 0;         // SPEC: L-BFGS ring head and scaling before the update made ahead of the
     double spec_bg0 = 1.0;      //       Lipschitz test (restored if the test fails after all)
@@ -557,6 +561,7 @@ L_outer_begin:   // ---- AlmOptimizer::step: project y on Y, then the inner prob
     }
     // PANOCEngine::init
     spec_fbe_ok = false;
+    spec_la_in = false;
     B.reset();
     I.iter = 0; num_iter = 0; cont = true;
     MPCB_FORJ { pt0[j] = I.u0[j]; pt1[j] = I.u1[j]; }
@@ -749,6 +754,15 @@ L_lip_check: {
             }
         }
         if (lane == 0) { SP->S = S; SP->gamma = I.gamma; SP->ceff = CS->c; }
+        if (!spec_la_in) {
+            // first line search of an inner problem: the look-ahead warp is idle (no request pending)
+            double* const lay = req + 8 * N + (size_t)2 * MPCB_SPEC_TRIALS * 6 * N;
+            MPCB_FORJ {
+                if (act[j]) { lay[lane + 32 * j] = I.ya[j]; lay[N + lane + 32 * j] = I.yw[j]; }
+            }
+            if (lane == 0) { SP->la_S = S; SP->la_ceff = CS->c; }
+            spec_la_in = true;
+        }
         for (;;) {
             spec_par ^= 1;
             if (lane == 0) { SP->ls0 = ls; SP->par = spec_par; SP->cmd = 1; }

@@ -111,7 +111,7 @@ typedef struct mpcb_solver_cfg {
                                   * AlmOptimizer::solve / PANOCOptimizer::solve do; exhausted ->
                                   * MPCB_NOT_CONVERGED_OUT_OF_TIME.  Results then depend on timing (as the
                                   * reference's do).  Honoured by the latency kernel, i.e. for batches of up to
-                                  * eight instances per SM and dims without team kernels - the single solve per
+                                  * twelve instances per SM and dims without team kernels - the single solve per
                                   * timestep; larger batches ignore it (max_inner_total is their budget).   */
 } mpcb_solver_cfg;
 
@@ -195,7 +195,7 @@ int32_t mpcb_eval_f64(const mpcb_dims* dims, const mpcb_robot* robot,
  *   evals[B,4]: {cost-only, cost+gradient} horizon evaluations the kernel performed
  *   (feeds the work/roofline accounting), the number of inner iterations that started
  *   with |gamma fpr| < tolerance but failed the AKKT test (so the solve went on), 0.
- * Kernel choice (results are bit-identical whichever runs, for a given dims/cfg): batches of at most eight
+ * Kernel choice (results are bit-identical whichever runs, for a given dims/cfg): batches of at most twelve
  * instances per SM - the single solve per timestep of the reference, small fleets - run the latency kernel (a CTA
  * per instance, line-search trials evaluated concurrently by helper warps); larger batches the
  * one-warp-per-instance queue kernel; dims with >= 64 ellipses (or cfg->team_mode = 1) the team kernels.
