@@ -486,7 +486,7 @@ def main():
                            "cpu_port_p50_ms": float(np.percentile(cpu_ms, 50)),
                            "cpu_port_p95_ms": float(np.percentile(cpu_ms, 95)), "cpu_solves": ncpu,
                            "what": "wall clock of solver().run(p) incl. H2D/D2H, one instance per call (latency kernel: a "
-                                   "eight-warp CTA on one SM, line-search trials evaluated concurrently, same bits as "
+                                   "six-warp CTA on one SM, line-search trials evaluated concurrently, same bits as "
                                    "the one-warp kernel), reference settings, no wall-clock cap; CPU port: one thread, "
                                    "same instances"}
 

@@ -284,7 +284,8 @@ struct SolveIO {
 // counters (only the trials up to the accepted one are counted) stay bit-identical to the one-warp
 // kernel and to the laned oracle.
 #ifndef MPCB_SPEC_TRIALS
-#define MPCB_SPEC_TRIALS 6       // measured: 4 -> 6 trials per batch, p95 of a single solve 79 -> 70 ms; 8 adds nothing
+#define MPCB_SPEC_TRIALS 4       // measured with the look-ahead warp (600 single solves; p50 / p95 ms): 3 trial
+                                 // warps 25.2 / 66.9, 4: 23.9 / 61.8, 5: 25.1 / 64.9, 6: 25.0 / 61.6
 #endif
 // warp 0 solves, warps 1..TRIALS evaluate line-search trials, the last warp evaluates the look-ahead cost
 constexpr int SPEC_THREADS = 32 * (2 + MPCB_SPEC_TRIALS);
