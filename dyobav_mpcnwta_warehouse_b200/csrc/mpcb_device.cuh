@@ -539,6 +539,14 @@ struct EvalOut {
 #ifndef MPCB_EVAL_ATTR
 #define MPCB_EVAL_ATTR __forceinline__
 #endif
+// -DMPCB_EVAL_PROF: clock64 segments of every evaluation, summed into the launch-profile area of the workspace
+// (scripts/eval_prof.py): rollout | reference path | speed, control, fleet | polygons | ellipses + F2 |
+// terminal, F2 gradient, accelerations, totals | adjoint; slot 7 counts evaluations
+#ifdef MPCB_EVAL_PROF
+#define EVAL_T(i) do { const long long t_ = clock64(); if (lane == 0 && P.prof) atomicAdd(P.prof + MPCB_WS_PROF_CTAS + 16000 + (i), (unsigned long long)(t_ - ev_t)); ev_t = clock64(); } while (0)
+#else
+#define EVAL_T(i) do { } while (0)
+#endif
 template <int SPL, int FIXED, bool TEAM = false>
 __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restrict__ S,
                                          const double (&v)[SPL], const double (&w)[SPL], double c,
@@ -562,6 +570,10 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
         act[j] = kk[j] < N;
     }
 
+#ifdef MPCB_EVAL_PROF
+    long long ev_t = clock64();
+    if (lane == 0 && P.prof) atomicAdd(P.prof + MPCB_WS_PROF_CTAS + 16007, 1ULL);
+#endif
     // ---- rollout: theta by prefix sum, then RK4 increments, then positions
     double dth[SPL], th[SPL], thn[SPL];
 #pragma unroll
@@ -670,6 +682,7 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
         const double x = X[j], y = Y[j];
         const float D = Df[j];
         double cst = 0.0, ggx = 0.0, ggy = 0.0;
+        EVAL_T(0);
 
         // -- reference path: qrpd * min_{i>=k} dist^2(p, seg_i)   (mpc_cost.py:84-95).
         //    Segments are visited from i = k; the walk stops once the precomputed bound
@@ -716,6 +729,7 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
                 ggy = 2.0 * qrpd * fma(vd, ddy, -vy);
             }
         }
+        EVAL_T(1);
         // -- speed reference + control effort (mpc_cost.py:46-53,78-79)
         {
             const double dv = v[j] - S[L.o_rv() + k];
@@ -766,6 +780,7 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
             cst = fma(1000.0, s1, cst);
             cst = fma(10.0, s2, cst);
         }
+        EVAL_T(2);
         // -- static polygons (mpc_builder.py:100-108)
         double sp = 0.0, spx = 0.0, spy = 0.0;
         if constexpr (!TEAM) {
@@ -802,6 +817,7 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
                 }
             }
         }
+        EVAL_T(3);
         // inactive lanes (steps beyond the horizon) carry no polygon hinge into F2
         cstj[j] = cst;
         gx[j] = ggx; gy[j] = ggy;
@@ -1004,6 +1020,7 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
         cost += cstj[j];
     }
 
+    EVAL_T(4);
     // ---- terminal cost on the last state (mpc_builder.py:148)
     double gthN = 0.0;
     {
@@ -1073,6 +1090,7 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
     out.f = need_f ? warp_sum(cost) : ps;
     out.f2sq = f2sq;
     out.psi = fma(hc, f2sq, ps);
+    EVAL_T(5);
 
     if (GRAD) {
         // adjoint: G = sum_{j>=k} g_j ; theta coupling via a second suffix sum
@@ -1103,6 +1121,7 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
             out.gv[j] = act[j] ? g0 : 0.0;
             out.gw[j] = act[j] ? g1 : 0.0;
         }
+        EVAL_T(6);
     }
 }
 
