@@ -786,6 +786,9 @@ L_lip_check: {
                     // counted, not used); the L-BFGS buffer is reset by the failing branch, ring head and
                     // scaling are put back, and the step goes on from the test as the one-warp kernel would
                     B.head = spec_head0; B.gamma = spec_bg0;
+#ifdef MPCB_SPEC_PROF
+                    if (lane == 0 && P.prof) atomicAdd(P.prof + MPCB_WS_PROF_CTAS + 16008, 1ULL);   // how often this path runs
+#endif
                     it_lip = 0;
                     want_grad = false;
                     spec_dir = false;
