@@ -212,12 +212,36 @@ __device__ __forceinline__ void lbfgs_apply(Lbfgs<SPL>& B, double (&q0)[SPL], do
     }
 }
 
+// warp_sum through shared memory: every lane reads the 32 partials and adds them in the butterfly's own
+// association ((i, i+16), then (i, i+8), ... - the tree every lane of the xor butterfly ends with), so the
+// bits are the same; for a warp that is alone on its scheduler the 31 independent-ish adds are shorter than
+// five dependent shuffle round trips.  (With 16 warps per SM the broadcast loads saturate the shared-memory
+// crossbar: round 1 measured -43 % there; this is for the latency kernel's solving warp only.)
+__device__ __forceinline__ double warp_sum_lds(double v, double* red, int lane)
+{
+    red[lane] = v;
+    __syncwarp();
+    const double2* r2 = reinterpret_cast<const double2*>(red);
+    double a[32];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { const double2 t = r2[i]; a[2 * i] = t.x; a[2 * i + 1] = t.y; }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = a[i] + a[i + 16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = a[i] + a[i + 8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = a[i] + a[i + 4];
+    a[0] = a[0] + a[2]; a[1] = a[1] + a[3];
+    __syncwarp();
+    return a[0] + a[1];
+}
+
 // The same recursion with the rows of the next step loaded before the reduction of the current one (the
 // latency kernel's lone solving warp has nothing else to cover the shared-memory latency with).  Same
 // operations in the same order: same bits.
 template <int SPL>
 __device__ __forceinline__ void lbfgs_apply_prefetch(Lbfgs<SPL>& B, double (&q0)[SPL], double (&q1)[SPL],
-                                                     int lane, const bool (&act)[SPL])
+                                                     int lane, const bool (&act)[SPL], double* red)
 {
     if (B.active == 0) return;
     double sv0[SPL], sv1[SPL], yv0[SPL], yv1[SPL], rho;
@@ -240,7 +264,7 @@ __device__ __forceinline__ void lbfgs_apply_prefetch(Lbfgs<SPL>& B, double (&q0)
         MPCB_FORJ { part = fma(sv0[j], q0[j], fma(sv1[j], q1[j], part)); c0[j] = yv0[j]; c1[j] = yv1[j]; }
         const double rk = rho;
         if (k + 1 < B.active) load(k + 1);
-        const double a = rk * warp_sum(part);
+        const double a = rk * warp_sum_lds(part, red, lane);
         if (lane == 0) B.alpha[row] = a;
         MPCB_FORJ { q0[j] = fma(-a, c0[j], q0[j]); q1[j] = fma(-a, c1[j], q1[j]); }
     }
@@ -254,7 +278,7 @@ __device__ __forceinline__ void lbfgs_apply_prefetch(Lbfgs<SPL>& B, double (&q0)
         MPCB_FORJ { part = fma(yv0[j], q0[j], fma(yv1[j], q1[j], part)); c0[j] = sv0[j]; c1[j] = sv1[j]; }
         const double rk = rho, al = B.alpha[row];
         if (k > 0) load(k - 1);
-        const double beta = rk * warp_sum(part);
+        const double beta = rk * warp_sum_lds(part, red, lane);
         const double cf = al - beta;
         MPCB_FORJ { q0[j] = fma(cf, c0[j], q0[j]); q1[j] = fma(cf, c1[j], q1[j]); }
     }
@@ -312,6 +336,7 @@ struct alignas(16) SpecShared {
     int cmd, ls0, par, la_cmd;     // par: which of the two result buffers the current batch fills
     int la_acc, la_par, pad0, pad1;   // look-ahead request: the half step of result (la_par, la_acc)
     double la_cost;                // ... and its answer
+    double red[32];                // the solving warp's reduction scratch (warp_sum_lds)
     double la_ceff;                // the look-ahead warp's own copy of what is constant over an inner problem
     const double* la_S;            // (written while that warp is idle: the first line search of the problem)
     double pad2;
@@ -663,7 +688,7 @@ L_step_begin:   // ---- PANOCEngine::step
             lbfgs_update<SPL>(P, B, I, lane, act);
             SPEC_T(6);
             MPCB_FORJ { I.d0[j] = I.r0[j]; I.d1[j] = I.r1[j]; }
-            lbfgs_apply_prefetch<SPL>(B, I.d0, I.d1, lane, act);
+            lbfgs_apply_prefetch<SPL>(B, I.d0, I.d1, lane, act, SP->red);
             SPEC_T(3);
             it_lip = 0;
             spec_dir = true;
