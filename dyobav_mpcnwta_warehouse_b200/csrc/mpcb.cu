@@ -598,7 +598,7 @@ __global__ void __launch_bounds__(TEAM_THREADS, MPCB_TEAM_CTAS) solve_kernel_tea
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x < TEAM_NS) {
         TeamShared* Ts = reinterpret_cast<TeamShared*>(base + (size_t)threadIdx.x * sstride + P.lb_doubles);
-        Ts->req = 0; Ts->done = 0; Ts->exit_ = 0;
+        Ts->req = 0; Ts->done = 0; Ts->exit_ = 0; Ts->pad[0] = (int)threadIdx.x;   // pad[0]: index of the solver
     }
     if (threadIdx.x == 0 && P.prof) {
         unsigned long long tns;
@@ -638,7 +638,7 @@ __global__ void __launch_bounds__(TEAM_THREADS, 1) eval_kernel_team(const KParam
     const int N = P.L.N;
     TeamPool* pool = reinterpret_cast<TeamPool*>(base + team_solver_doubles(N));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) { T->req = 0; T->done = 0; T->exit_ = 0; }
+    if (threadIdx.x == 0) { T->req = 0; T->done = 0; T->exit_ = 0; T->pad[0] = 0; }
     __syncthreads();
     if (warp >= TEAM_NS) { team_worker<0>(P, base, team_solver_doubles(N), 0, 1, pool, (int)threadIdx.x - 32 * TEAM_NS); return; }
     if (warp != 0) return;

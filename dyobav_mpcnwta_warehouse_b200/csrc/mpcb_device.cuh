@@ -667,7 +667,13 @@ __device__ MPCB_EVAL_ATTR void eval_psi(const KParams& P, const double* __restri
             T->req = r;
         }
         __syncwarp();
+#ifdef MPCB_TEAM_BAR_WAIT
+        // blocked on a named barrier the pool's first warp arrives at, instead of spinning on the flag: a
+        // waiting solver warp then takes no issue slots from the workers of its scheduler
+        bar_sync(8 + T->pad[0], 64);
+#else
         while (T->done != r) { MPCB_SPIN_SOLVER; }
+#endif
         __threadfence_block();
         __syncwarp();
     }
@@ -1381,6 +1387,12 @@ __device__ __forceinline__ void team_worker(const KParams& P, double* solvers, i
             __threadfence_block();
             T->done = T->req;
         }
+#ifdef MPCB_TEAM_BAR_WAIT
+        if (t < 32) {
+            __syncwarp();
+            asm volatile("bar.arrive %0, %1;" ::"r"(8 + cur), "n"(64) : "memory");
+        }
+#endif
     }
 }
 
